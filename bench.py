@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the LightGCN hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+ours:       one "step" = one fused train step (K-layer propagation + BPR + backward
+            + Adam) on one batch of B=2048 triples of the cfg-2 graph
+            (BASELINE.json configs[1]); `value` = nnz(A_hat) * layers / t_step with
+            inputs resident in HBM, `e2e` = the same through LightGCN.stageOne()
+            with pinned HOST triples (H2D inside) and a D2H read of the loss.
+            The eval half of the metric (full-rank top-20 users/s) rides in "eval".
+reference:  the reference's CPU path (torch.sparse.mm xK + autograd + Adam, the
+            oracle port of model/lgcn.py:127-133) on this box's host cores.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+METRIC = "LightGCN train edges*layers/sec (prop+BPR)"
+UNIT = "edges*layers/s"
+CFG2 = dict(n_users=30000, m_items=41000, n_interactions=1_250_000, seed=2020, d=64, layers=3, batch=2048,
+            lr=1e-4, decay=1e-7)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--storage", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1424.4))), "measured"
+    return 6650.0, 1400.0, "fallback"  # B200_PROFILING.md fallback figures
+
+
+def spmm_layer_bytes(nnz: int, N: int, d: int, s: int) -> int:
+    """col ids + gathered rows + write Z + read/write fp32 layer sum + rowptr."""
+    return nnz * (4 + d * s) + N * d * s + 2 * N * d * 4 + (N + 1) * 8
+
+
+# ------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_train_steps(ds_arrays, steps: int, warmup: int, threads: int):
+    """The reference's CPU path (oracle port): unsplit torch.sparse.mm graph, autograd, torch Adam."""
+    import numpy as np
+    import torch
+    from oracle import lgcn_oracle as orc
+    torch.set_num_threads(threads)
+    n, m, tu, ti = ds_arrays
+    g = torch.Generator().manual_seed(2020)
+    E = torch.randn(n + m, CFG2["d"], generator=g) * 0.1
+    om = orc.OracleModel(n, m, tu, ti, E, CFG2["layers"], CFG2["lr"], CFG2["decay"])
+    rng = np.random.default_rng(0)
+    B = CFG2["batch"]
+    times = []
+    for s in range(warmup + steps):
+        idx = rng.integers(0, len(tu), B)
+        users = torch.from_numpy(tu[idx]); pos = torch.from_numpy(ti[idx])
+        neg = torch.from_numpy(rng.integers(0, m, B))
+        t0 = time.perf_counter()
+        om.stage_one(users, pos, neg)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    import torch
+    from furusato_recommend_b200.synthetic import bipartite
+    n, m, tu, ti, su, si = bipartite(CFG2["n_users"], CFG2["m_items"], CFG2["n_interactions"], seed=CFG2["seed"])
+    nnz = 2 * int(tu.numel())
+    threads = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 10))  # ~1 s per CPU step: keep the arm within a few minutes
+    warm = max(1, min(args.warmup, 2))
+    t = cpu_train_steps((n, m, tu.numpy(), ti.numpy()), steps, warm, threads)
+    val = nnz * CFG2["layers"] / t
+    sample = f"{steps} stageOne steps ({warm} warm-up) of the cfg-2 graph, unsplit torch.sparse.mm, B={CFG2['batch']}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg-2: LightGCN 3-layer d=64 BPR B=2048, synthetic five-core bipartite graph "
+                               f"{n}x{m}, nnz={nnz}", "path": "reference CPU path (oracle port, torch.sparse)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from furusato_recommend_b200 import LightGCN, UniformSample, Trainer
+    from furusato_recommend_b200.dataloader import BasicDataset
+    from furusato_recommend_b200.synthetic import bipartite
+    from furusato_recommend_b200 import ops, metric as lmetric
+
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    # weak scaling: every rank trains its own cfg-2-sized graph shard (seed differs per rank)
+    n, m, tu, ti, su, si = bipartite(CFG2["n_users"], CFG2["m_items"], CFG2["n_interactions"], seed=CFG2["seed"] + rank)
+    cfg = dict(recdim=CFG2["d"], layer=CFG2["layers"], lr=CFG2["lr"], decay=CFG2["decay"],
+               bpr_batch_size=CFG2["batch"], device=dev, test_u_batch_size=10000, storage_dtype=args.storage)
+    ds = BasicDataset(n, m, tu.numpy(), ti.numpy(), su.numpy(), si.numpy(), config=cfg, device=dev)
+    torch.manual_seed(2020 + rank)
+    model = LightGCN(cfg, ds)
+    model.train()
+    N, nnz, K, d, B = n + m, model.graph.nnz, CFG2["layers"], CFG2["d"], CFG2["batch"]
+
+    S = UniformSample(ds, seed=CFG2["seed"], epoch=0)
+    n_batches = len(S) // B
+    users, pos, neg = (S[:, j].contiguous() for j in range(3))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(i):
+        b = (i % n_batches) * B
+        model._fused_step(users[b:b + B], pos[b:b + B], neg[b:b + B])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)            # L2 flush between timed iterations (untimed)
+        ev[i][0].record()
+        step(args.warmup + i)
+        ev[i][1].record()
+    barrier()
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3  # seconds for K steps
+
+    # ---- per-launch SpMM time, live, with events around every propagate launch ----
+    spmm_ms = []
+    orig = ops.propagate_layer
+
+    def timed_layer(*a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); orig(*a, **kw); e1.record()
+        spmm_ms.append((e0, e1))
+    import furusato_recommend_b200.model as _m
+    _m.ops.propagate_layer = timed_layer
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        step(i)
+    torch.cuda.synchronize()
+    _m.ops.propagate_layer = orig
+    spmm_avg_s = sum(a.elapsed_time(b) for a, b in spmm_ms) / len(spmm_ms) / 1e3
+
+    # ---- e2e: public API with pinned host triples, H2D + loss D2H inside the timed region ----
+    S_host = S.cpu()
+    hu, hp, hn = (S_host[:, j].contiguous().pin_memory() for j in range(3))
+    for i in range(3):
+        model.stageOne(hu[:B], hp[:B], hn[:B]).item()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        b = (i % n_batches) * B
+        loss = model.stageOne(hu[b:b + B], hp[b:b + B], hn[b:b + B])
+        loss.item()
+    e1.record()
+    barrier()
+    t_e2e = e0.elapsed_time(e1) / 1e3
+    clk = clocks.stop()
+
+    # ---- eval half of the metric: full-rank top-20 users/s ----
+    eval_info = None
+    if not args.no_eval:
+        model.eval()
+        tr = Trainer(cfg, ds, model)
+        ev_users = tr._eval_users()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(); model.computer(); p1.record()
+        rp, srt = ds.test_csr()
+        tr.test()  # warm-up
+        reps = 3
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(reps):
+            sums = torch.zeros((4, 2), dtype=torch.float64, device=dev)
+            for s0 in range(0, len(ev_users), 10000):
+                bu = ev_users[s0:s0 + 10000]
+                idx, _ = model.getUsersTopK(bu, 20)
+                lmetric.batch_metric_sums(idx, bu, rp, srt, (10, 20), sums)
+        a1.record()
+        torch.cuda.synchronize()
+        t_eval = a0.elapsed_time(a1) / 1e3 / reps
+        hosts = torch.from_numpy(ds.test_users()).pin_memory()
+        w0 = time.perf_counter()
+        res = tr.test()  # public API: host user ids in, metric dict out
+        torch.cuda.synchronize()
+        t_eval_e2e = time.perf_counter() - w0
+        peak_tf = measured_peaks()[1]
+        flops = 2.0 * len(ev_users) * m * d
+        eval_info = {"metric": "full-rank top-20 eval users/sec (score+mask+top-k+metrics)",
+                     "value": len(ev_users) / t_eval, "unit": "users/s", "users": int(len(ev_users)), "items": m,
+                     "precision": model.eval_precision, "propagation_ms": p0.elapsed_time(p1),
+                     "e2e": {"value": len(ev_users) / t_eval_e2e, "unit": "users/s"},
+                     "tflops": flops / t_eval / 1e12, "tensor_peak_tflops": peak_tf,
+                     "recall@20": float(res["recall"][1]), "ndcg@20": float(res["ndcg"][1])}
+        model.train()
+
+    # ---- max over ranks ----
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e, spmm_avg_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, spmm_avg_s = (float(x) for x in t)
+        tot = torch.tensor([float(nnz)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tot)
+        nnz_total = float(tot)
+    else:
+        nnz_total = float(nnz)
+
+    if rank == 0:
+        hbm_peak, _, which = measured_peaks()
+        s_bytes = 2 if args.storage == "bf16" else 4
+        layer_bytes = spmm_layer_bytes(nnz, N, d, s_bytes)
+        achieved = layer_bytes / spmm_avg_s / 1e9
+        traffic = None
+        tp = REPO / "profiles" / "spmm_traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get(f"dram_bytes_per_launch_{args.storage}")
+        ms = t_dev / args.steps * 1e3
+        out = {
+            "metric": METRIC, "value": nnz_total * K / (t_dev / args.steps), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.storage == "fp32" else "bf16-storage/f32-acc",
+            "data": "synthetic",
+            "config": {"workload": f"cfg-2: LightGCN {K}-layer d={d} BPR B={B} on a synthetic five-core bipartite graph "
+                                   f"{n} users x {m} items, nnz(A_hat)={nnz} per GPU",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush, untimed)",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent cfg-2 graph shards (no collective)"},
+            "e2e": {"value": nnz_total * K / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 3 * B * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": (2 * K + 2) * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "spmm_layer_kernel", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which,
+                         "bytes_per_launch": layer_bytes, "avg_launch_us": spmm_avg_s * 1e6,
+                         "launches_per_step": 2 * K,
+                         "note": "gather model; the 18 MB table is L2-resident at cfg-2 so frac may exceed 1"},
+            "clocks": clk,
+        }
+        if eval_info:
+            out["eval"] = eval_info
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            t_cpu = cpu_train_steps((n, m, tu.numpy(), ti.numpy()), 5, 2, threads)
+            out["cpu_baseline"] = {"value": nnz * K / t_cpu, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": "5 stageOne steps (2 warm-up) of the same cfg-2 graph on the host: unsplit "
+                                             "torch.sparse.mm x3 + autograd + torch Adam, B=2048",
+                                   "ms_per_step": t_cpu * 1e3}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,417 @@
+// K-layer LightGCN propagation: CSR SpMM with the symmetric normalisation folded
+// into dinv, fused with the layer-sum / Horner / Adam row epilogue.
+//
+// Replaces torch.sparse.mm (reference model/MF.py:200,204), PyG LGConv
+// (model/lgcn.py:82), the layer mean (model/lgcn.py:83-84) and, in grad_mode 2,
+// optim.Adam.step() (model/lgcn.py:132).  See include/lgcn_b200.h for the maths.
+//
+// Work decomposition (HBM/L2-gather bound, no tensor cores):
+//   * a "group" of LPR = row_bytes/16 lanes owns one light row (deg <= HUB_DEG):
+//     every lane keeps 16 bytes of the row in registers, so one gathered
+//     neighbour row is one fully coalesced LPR*16-byte request;
+//   * column indices are fetched LPR at a time (one coalesced load per group),
+//     broadcast with shuffles, and the next chunk is prefetched while up to
+//     UNROLL neighbour rows are in flight per lane;
+//   * rows longer than HUB_DEG are cut into CTA-wide segments (<= SEG_EDGES
+//     edges): the CTA's groups stride over the segment, reduce through shared
+//     memory in a fixed order, and multi-segment hubs are finished by the last
+//     arriving CTA which adds the partials in segment order (deterministic);
+//   * light rows are visited in degree-descending order so the longest chains
+//     start first and the tail of the grid is made of cheap rows.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace lgcn {
+
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+constexpr int kBlock = 256;
+
+template <int D, bool SRC_BF16>
+struct RowCfg {
+  static constexpr int kRowBytes = D * (SRC_BF16 ? 2 : 4);
+  static constexpr int kLPR = kRowBytes / 16;          // lanes per row
+  static constexpr int kEPL = SRC_BF16 ? 8 : 4;        // elements per lane
+  static constexpr int kGroups = kBlock / kLPR;        // groups per CTA
+  static constexpr int kUnroll = kLPR >= 8 ? 8 : kLPR; // neighbour rows in flight
+  static_assert(kRowBytes % 16 == 0 && kLPR >= 2 && kLPR <= 32, "unsupported row width");
+  static_assert((kLPR & (kLPR - 1)) == 0, "lanes per row must be a power of two");
+};
+
+struct GraphDev {
+  const int64_t* rowptr;
+  const int32_t* col;
+  const float* dinv;
+  const int32_t* light_rows;
+  int64_t n_light;
+  const int32_t* seg_row;
+  const int64_t* seg_begin;
+  const int32_t* seg_len;
+  const int32_t* seg_hub;
+  int n_seg;
+  const int32_t* hub_seg0;
+  const int32_t* hub_nseg;
+  int32_t* hub_counter;
+  float* partial;
+};
+
+struct EpiDev {
+  const void* src;
+  void* dst;
+  const float* base;
+  const float* acc_in;
+  float* acc_out;
+  float acc_scale;
+  int grad_mode;
+  float inv_layers;
+  float reg_coef;
+  int32_t* cnt;
+  float* emb;
+  float* grad;
+  float* adam_m;
+  float* adam_v;
+  const float* adam_hp;
+  float one_minus_b1, beta2, one_minus_b2, eps;
+  int zero_base;
+};
+
+// Sum of w_j * SRC[col[e]] over e = e0, e0+1, .. inside [e0, e_end) taken in
+// chunks of LPR edges that advance by `stride` edges (stride == LPR: the whole
+// range; stride == kGroups*LPR: this group's share of a hub segment).
+template <int D, bool SRC_BF16, bool SCALE_SRC>
+__device__ __forceinline__ void gather_sum(const void* __restrict__ src,
+                                           const int32_t* __restrict__ col,
+                                           const float* __restrict__ dinv, int64_t e0,
+                                           int64_t e_end, int64_t stride, int lig, unsigned gmask,
+                                           float (&acc)[RowCfg<D, SRC_BF16>::kEPL]) {
+  using C = RowCfg<D, SRC_BF16>;
+  constexpr int LPR = C::kLPR, EPL = C::kEPL, U = C::kUnroll;
+  const char* rows = reinterpret_cast<const char*>(src) + lig * 16;
+
+  int nxt_c = 0;
+  float nxt_w = 0.f;
+  if (e0 + lig < e_end) {
+    nxt_c = ldg_stream_i32(col + e0 + lig);
+    if (SCALE_SRC) nxt_w = __ldg(dinv + nxt_c);
+  }
+  for (int64_t e = e0; e < e_end; e += stride) {
+    const int cnt = (e_end - e) < LPR ? int(e_end - e) : LPR;
+    const int cur_c = nxt_c;
+    const float cur_w = nxt_w;
+    const int64_t en = e + stride;
+    if (en + lig < e_end) {  // prefetch the next chunk of column ids
+      nxt_c = ldg_stream_i32(col + en + lig);
+      if (SCALE_SRC) nxt_w = __ldg(dinv + nxt_c);
+    }
+    for (int t = 0; t < cnt; t += U) {
+      uint4 v[U];
+      float w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = __shfl_sync(gmask, cur_c, t + u, LPR);
+        if (SCALE_SRC) w[u] = __shfl_sync(gmask, cur_w, t + u, LPR);
+        if (t + u < cnt) {
+          v[u] = ldg_row16(rows + (int64_t)c * C::kRowBytes);
+        } else {
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (SCALE_SRC) w[u] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (SRC_BF16) {
+          float f[8];
+          unpack_bf16x8(v[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j % EPL] += f[j];
+        } else {
+          const float f[4] = {__uint_as_float(v[u].x), __uint_as_float(v[u].y),
+                              __uint_as_float(v[u].z), __uint_as_float(v[u].w)};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (SCALE_SRC) acc[j] = fmaf(w[u], f[j], acc[j]);
+            else acc[j] += f[j];
+          }
+        }
+      }
+    }
+  }
+}
+
+// Row epilogue; lane `lig` holds s[0..EPL) = elements [lig*EPL, lig*EPL+EPL) of row.
+template <int D, int EPL, bool DST_BF16>
+__device__ __forceinline__ void row_epilogue(const EpiDev& p, const float* __restrict__ dinv,
+                                             int64_t row, int lig, unsigned gmask,
+                                             const float (&s)[EPL]) {
+  const float di = __ldg(dinv + row);
+  const int64_t off = row * D + lig * EPL;
+  float x[EPL], t[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) x[j] = di * s[j];
+
+  if (p.base != nullptr) {
+#pragma unroll
+    for (int q = 0; q < EPL / 4; ++q) {
+      const float4 b = ld_f4(p.base + off + 4 * q);
+      t[4 * q + 0] = b.x + x[4 * q + 0];
+      t[4 * q + 1] = b.y + x[4 * q + 1];
+      t[4 * q + 2] = b.z + x[4 * q + 2];
+      t[4 * q + 3] = b.w + x[4 * q + 3];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) t[j] = x[j];
+  }
+
+  if (p.dst != nullptr) {
+    float z[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) z[j] = di * t[j];
+    if (DST_BF16) {
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.dst) + off;
+      if (EPL == 8) {
+        float z8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z8[j] = z[j % EPL];
+        st_u4(dp, pack_bf16x8(z8));
+      } else {
+        uint2 w2;
+        w2.x = pack_bf16x2(z[0], z[1]);
+        w2.y = pack_bf16x2(z[2], z[3]);
+        *reinterpret_cast<uint2*>(dp) = w2;
+      }
+    } else {
+      float* dp = reinterpret_cast<float*>(p.dst) + off;
+#pragma unroll
+      for (int q = 0; q < EPL / 4; ++q)
+        st_f4(dp + 4 * q, make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]));
+    }
+  }
+
+  if (p.acc_out != nullptr) {
+#pragma unroll
+    for (int q = 0; q < EPL / 4; ++q) {
+      const float4 a = ld_f4(p.acc_in + off + 4 * q);
+      st_f4(p.acc_out + off + 4 * q,
+            make_float4((a.x + x[4 * q + 0]) * p.acc_scale, (a.y + x[4 * q + 1]) * p.acc_scale,
+                        (a.z + x[4 * q + 2]) * p.acc_scale, (a.w + x[4 * q + 3]) * p.acc_scale));
+    }
+  }
+
+  if (p.grad_mode != 0) {
+    const float rc = p.reg_coef * float(p.cnt[row]);
+    float step_size = 0.f, bc2_sqrt = 1.f;
+    if (p.grad_mode == 2) {
+      step_size = __ldg(p.adam_hp);
+      bc2_sqrt = __ldg(p.adam_hp + 1);
+    }
+#pragma unroll
+    for (int q = 0; q < EPL / 4; ++q) {
+      const float4 e4 = ld_f4(p.emb + off + 4 * q);
+      const float e[4] = {e4.x, e4.y, e4.z, e4.w};
+      float g[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = fmaf(rc, e[j], t[4 * q + j] * p.inv_layers);
+      if (p.grad_mode == 1) {
+        st_f4(p.grad + off + 4 * q, make_float4(g[0], g[1], g[2], g[3]));
+      } else {
+        const float4 m4 = ld_f4(p.adam_m + off + 4 * q);
+        const float4 v4 = ld_f4(p.adam_v + off + 4 * q);
+        float m[4] = {m4.x, m4.y, m4.z, m4.w};
+        float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        float en[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          m[j] = fmaf(g[j] - m[j], p.one_minus_b1, m[j]);
+          v[j] = fmaf(p.one_minus_b2 * g[j], g[j], v[j] * p.beta2);
+          const float denom = sqrtf(v[j]) / bc2_sqrt + p.eps;
+          en[j] = e[j] - step_size * (m[j] / denom);
+        }
+        st_f4(p.adam_m + off + 4 * q, make_float4(m[0], m[1], m[2], m[3]));
+        st_f4(p.adam_v + off + 4 * q, make_float4(v[0], v[1], v[2], v[3]));
+        st_f4(p.emb + off + 4 * q, make_float4(en[0], en[1], en[2], en[3]));
+        if (p.zero_base)  // leave G clean for the next step's scatter
+          st_f4(const_cast<float*>(p.base) + off + 4 * q, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
+    if (p.grad_mode == 2) {
+      __syncwarp(gmask);  // every lane of the group has read cnt[row]
+      if (lig == 0) p.cnt[row] = 0;
+    }
+  }
+}
+
+template <int D, bool SRC_BF16, bool DST_BF16, bool SCALE_SRC>
+__global__ void __launch_bounds__(kBlock) spmm_layer_kernel(const GraphDev g, const EpiDev p) {
+  using C = RowCfg<D, SRC_BF16>;
+  constexpr int LPR = C::kLPR, EPL = C::kEPL, NG = C::kGroups;
+  const int lig = threadIdx.x % LPR;   // lane in group
+  const int grp = threadIdx.x / LPR;   // group in CTA
+  const unsigned gmask = group_mask(LPR);
+
+  float acc[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) acc[j] = 0.f;
+
+  if ((int)blockIdx.x >= g.n_seg) {
+    // ---------------- light rows: one group per row ----------------
+    const int64_t gid = (int64_t)(blockIdx.x - g.n_seg) * NG + grp;
+    if (gid >= g.n_light) return;
+    const int64_t row = g.light_rows[gid];
+    const int64_t b = g.rowptr[row], e = g.rowptr[row + 1];
+    gather_sum<D, SRC_BF16, SCALE_SRC>(p.src, g.col, g.dinv, b, e, LPR, lig, gmask, acc);
+    row_epilogue<D, EPL, DST_BF16>(p, g.dinv, row, lig, gmask, acc);
+    return;
+  }
+
+  // ---------------- hub segment: the whole CTA on <= SEG_EDGES edges ----------------
+  __shared__ float red[NG][D];
+  __shared__ int s_last;
+  const int seg = blockIdx.x;
+  const int64_t row = g.seg_row[seg];
+  const int64_t b = g.seg_begin[seg];
+  const int64_t e = b + g.seg_len[seg];
+  gather_sum<D, SRC_BF16, SCALE_SRC>(p.src, g.col, g.dinv, b + (int64_t)grp * LPR, e,
+                                     (int64_t)NG * LPR, lig, gmask, acc);
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) red[grp][lig * EPL + j] = acc[j];
+  __syncthreads();
+  float colsum = 0.f;
+  if (threadIdx.x < D) {
+#pragma unroll 8
+    for (int q = 0; q < NG; ++q) colsum += red[q][threadIdx.x];
+  }
+  const int hub = g.seg_hub[seg];
+  const int nseg = g.hub_nseg[hub];
+  if (nseg > 1) {
+    const int seg0 = g.hub_seg0[hub];
+    if (threadIdx.x < D) g.partial[(int64_t)seg * D + threadIdx.x] = colsum;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int old = atomicAdd(g.hub_counter + hub, 1);
+      s_last = (old == nseg - 1);
+      if (old == nseg - 1) g.hub_counter[hub] = 0;  // self-reset for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < D) {
+      colsum = 0.f;
+      for (int q = 0; q < nseg; ++q)
+        colsum += __ldcg(g.partial + (int64_t)(seg0 + q) * D + threadIdx.x);
+    }
+  }
+  __syncthreads();  // everyone is done reading red[*] before it is overwritten
+  if (threadIdx.x < D) red[0][threadIdx.x] = colsum;
+  __syncthreads();
+  if (grp == 0) {
+    float s[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) s[j] = red[0][lig * EPL + j];
+    row_epilogue<D, EPL, DST_BF16>(p, g.dinv, row, lig, gmask, s);
+  }
+}
+
+template <int D, bool SRC_BF16, bool DST_BF16, bool SCALE_SRC>
+static int launch_layer(const GraphDev& g, const EpiDev& p, cudaStream_t st) {
+  using C = RowCfg<D, SRC_BF16>;
+  static_assert(D <= kBlock, "hub reduction assumes D <= block size");
+  const int64_t light_blocks = (g.n_light + C::kGroups - 1) / C::kGroups;
+  const int64_t grid = (int64_t)g.n_seg + light_blocks;
+  if (grid == 0) return 0;
+  if (grid > 0x7fffffffLL) {
+    set_last_error("grid too large: %lld", (long long)grid);
+    return LGCN_ERR_UNSUPPORTED;
+  }
+  spmm_layer_kernel<D, SRC_BF16, DST_BF16, SCALE_SRC><<<(unsigned)grid, kBlock, 0, st>>>(g, p);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
+template <int D>
+static int dispatch_dtype(const lgcn_layer_args_t* a, const GraphDev& g, const EpiDev& p,
+                          cudaStream_t st) {
+  const bool sb = a->src_dtype == LGCN_BF16, db = a->dst_dtype == LGCN_BF16;
+  if (!sb && !db) {
+    return a->scale_src ? launch_layer<D, false, false, true>(g, p, st)
+                        : launch_layer<D, false, false, false>(g, p, st);
+  }
+  if (!sb && db) {
+    return a->scale_src ? launch_layer<D, false, true, true>(g, p, st)
+                        : launch_layer<D, false, true, false>(g, p, st);
+  }
+  if (sb && db) {
+    if (a->scale_src) {
+      set_last_error("scale_src needs an fp32 source");
+      return LGCN_ERR_UNSUPPORTED;
+    }
+    return launch_layer<D, true, true, false>(g, p, st);
+  }
+  set_last_error("bf16 source with fp32 destination is not a LightGCN layer");
+  return LGCN_ERR_UNSUPPORTED;
+}
+
+}  // namespace lgcn
+
+using namespace lgcn;
+
+extern "C" int lgcn_abi_version(void) { return LGCN_ABI_VERSION; }
+extern "C" const char* lgcn_last_error(void) { return lgcn::last_error(); }
+
+extern "C" int lgcn_propagate_layer(const lgcn_graph_t* gh, const lgcn_layer_args_t* a,
+                                    lgcn_stream_t stream) {
+  LGCN_CHECK_ARG(gh != nullptr && a != nullptr, "null graph/args");
+  LGCN_CHECK_ARG(gh->n_nodes >= 0 && gh->n_nodes < 0x7fffffffLL, "n_nodes must fit int32");
+  LGCN_CHECK_ARG(a->src != nullptr, "src is null");
+  LGCN_CHECK_ARG(gh->n_seg < 0x7fffffffLL, "too many hub segments");
+  LGCN_CHECK_ARG(a->acc_out == nullptr || a->acc_in != nullptr, "acc_out needs acc_in");
+  LGCN_CHECK_ARG(a->grad_mode >= 0 && a->grad_mode <= 2, "grad_mode must be 0, 1 or 2");
+  if (a->grad_mode != 0) {
+    LGCN_CHECK_ARG(a->emb != nullptr && a->cnt != nullptr, "grad_mode needs emb and cnt");
+    LGCN_CHECK_ARG(a->grad_mode != 1 || a->grad != nullptr, "grad_mode 1 needs grad");
+    LGCN_CHECK_ARG(a->grad_mode != 2 || (a->adam_m && a->adam_v && a->adam_hp && a->base),
+                   "grad_mode 2 needs adam_m, adam_v, adam_hp and base");
+  }
+  if (gh->n_nodes == 0) return 0;
+
+  GraphDev g;
+  g.rowptr = gh->rowptr; g.col = gh->col; g.dinv = gh->dinv;
+  g.light_rows = gh->light_rows; g.n_light = gh->n_light;
+  g.seg_row = gh->seg_row; g.seg_begin = gh->seg_begin; g.seg_len = gh->seg_len;
+  g.seg_hub = gh->seg_hub; g.n_seg = (int)gh->n_seg;
+  g.hub_seg0 = gh->hub_seg0; g.hub_nseg = gh->hub_nseg; g.hub_counter = gh->hub_counter;
+  g.partial = gh->partial;
+
+  EpiDev p;
+  p.src = a->src; p.dst = a->dst; p.base = a->base;
+  p.acc_in = a->acc_in; p.acc_out = a->acc_out; p.acc_scale = a->acc_scale;
+  p.grad_mode = a->grad_mode; p.inv_layers = a->inv_layers; p.reg_coef = a->reg_coef;
+  p.cnt = a->cnt; p.emb = a->emb; p.grad = a->grad;
+  p.adam_m = a->adam_m; p.adam_v = a->adam_v; p.adam_hp = a->adam_hp;
+  p.one_minus_b1 = (float)(1.0 - a->beta1);
+  p.beta2 = (float)a->beta2;
+  p.one_minus_b2 = (float)(1.0 - a->beta2);
+  p.eps = (float)a->eps;
+  p.zero_base = a->zero_base;
+  LGCN_CHECK_ARG(!(a->zero_base && a->base == a->src), "zero_base with src == base races");
+
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->d) {
+    case 32: return dispatch_dtype<32>(a, g, p, st);
+    case 64: return dispatch_dtype<64>(a, g, p, st);
+    case 128: return dispatch_dtype<128>(a, g, p, st);
+    default:
+      set_last_error("unsupported embedding width d=%d (supported: 32, 64, 128)", a->d);
+      return LGCN_ERR_UNSUPPORTED;
+  }
+}

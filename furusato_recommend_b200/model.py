@@ -1,0 +1,318 @@
+"""LightGCN with the reference's model API on hand-written sm_100a kernels.
+
+Same duck-typed surface as reference model/lgcn.py:44-151 (`forward()`,
+`getEmbedding`, `bpr_loss`, `getUsersRating`, `stageOne`, `OneEpoch`, owns
+`self.optim`, state-dict key `all_embedding.weight` with users first) plus
+`computer()` — the name the same computation has on the legacy torch.sparse class
+(model/MF.py:178-210) — and the fused, never-materialised eval entry
+`getUsersTopK()`.
+
+Two ways through the training step:
+  * `stageOne()` / `OneEpoch()`: the fused path.  2K SpMM launches + 1 BPR launch
+    + 1 tiny Adam tick; the layer mean, the Horner backward, the L2 term, the
+    G/cnt reset and Adam all live in kernel epilogues.  No autograd involved.
+  * `bpr_loss()` + `.backward()` + `optim.step()`: autograd-compatible for
+    callers that drive the optimizer themselves (reference ddp_lgcn.py:498-504);
+    the same kernels behind `torch.autograd.Function`s.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from .dataloader import BasicDataset
+from .graph import CsrGraph
+
+_STORAGE = {"fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """Adam (default betas/eps, no weight decay — reference model/lgcn.py:63) whose
+    state lives in flat device buffers the fused kernels update in place.  `step()`
+    applies lgcn_adam_step to `.grad` for the autograd path."""
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    def _init_state(self, p: torch.Tensor) -> dict:
+        st = self.state[p]
+        if not st:
+            st["step"] = torch.zeros(1, dtype=torch.int64, device=p.device)
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            st["hp"] = torch.zeros(2, dtype=torch.float32, device=p.device)
+        return st
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self._init_state(p)
+                ops.adam_tick(st["step"], st["hp"], group["lr"], group["betas"])
+                ops.adam_step(p.data, p.grad.contiguous(), st["exp_avg"], st["exp_avg_sq"], st["hp"],
+                              group["betas"], group["eps"])
+        return loss
+
+
+class _PropagateFn(torch.autograd.Function):
+    """OUT = mean_k A_hat^k E; backward is the same operator (A_hat symmetric)."""
+
+    @staticmethod
+    def forward(ctx, weight: torch.Tensor, model: "LightGCN"):
+        ctx.model = model
+        out = torch.empty_like(weight)
+        model._propagate_into(weight.detach(), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        m: "LightGCN" = ctx.model
+        grad = torch.empty_like(grad_out)
+        m._horner_into(grad_out.contiguous(), grad_mode=1, reg_coef=0.0, grad=grad, cnt=m._zero_cnt())
+        return grad, None
+
+
+class _BprFn(torch.autograd.Function):
+    """(loss, reg) = bpr_loss(E; users,pos,neg) with the closed-form backward."""
+
+    @staticmethod
+    def forward(ctx, weight: torch.Tensor, model: "LightGCN", users, pos, neg):
+        m = model
+        m._propagate_into(weight.detach(), m._buf("OUT"))
+        m._eval_cache_valid = False
+        m._reset_seed_buffers()
+        lo = m._buf("loss_out")
+        ops.bpr_fwd_bwd(m._buf("OUT"), weight.detach(), users, pos, neg, m.num_users, 0.0,
+                        m._buf("G"), m._buf("cnt"), lo, m._work(users.numel()), m._buf("work_counter"))
+        m._g_clean = False
+        m._seed_generation += 1
+        ctx.model, ctx.gen, ctx.batch = m, m._seed_generation, users.numel()
+        return lo[0].clone(), lo[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_loss: torch.Tensor, g_reg: torch.Tensor):
+        m: "LightGCN" = ctx.model
+        if ctx.gen != m._seed_generation:
+            raise RuntimeError("bpr_loss() was called again before backward(): the gradient seed is stale")
+        gl, gr = float(g_loss), float(g_reg)
+        G = m._buf("G")
+        if gl != 1.0:
+            G.mul_(gl)
+        grad = torch.empty_like(m.all_embedding.weight)
+        m._horner_into(G, grad_mode=1, reg_coef=gr / ctx.batch, grad=grad, cnt=m._buf("cnt"))
+        return grad, None, None, None, None
+
+
+class LightGCN(nn.Module):
+    def __init__(self, config: dict, dataset: BasicDataset):
+        super().__init__()
+        self.config = config
+        self.dataset = dataset
+        self.num_users = dataset.n_users
+        self.num_items = dataset.m_items
+        # reference keys (model/lgcn.py:51-52) with the legacy aliases (model/MF.py:126-127)
+        self.latent_dim = int(config["recdim"] if "recdim" in config else config["latent_dim_rec"])
+        self.num_layers = int(config["layer"] if "layer" in config else config["lightGCN_n_layers"])
+        if self.num_layers < 1:
+            raise NotImplementedError("layer=0 is plain matrix factorisation, outside the LightGCN hot path")
+        self.device = torch.device(config.get("device", "cuda:0"))
+        self.storage_dtype = _STORAGE[config.get("storage_dtype", "fp32")]
+        self.eval_precision = config.get("eval_precision", "fp32")
+        self.graph: CsrGraph = dataset.csr_graph()
+        if self.graph.device != self.device:
+            self.graph = self.graph.to(self.device)
+        self.__init_weight()
+        self.optim = FusedAdam(self.parameters(), lr=config["lr"])  # model/lgcn.py:63
+        self._bufs = {}
+        self._g_clean = True
+        self._seed_generation = 0
+        self._eval_cache_valid = False
+
+    def train(self, mode: bool = True):
+        # weights only move in training mode; eval mode may reuse one propagation
+        # for every user batch (the reference re-propagates per batch, model/lgcn.py:121)
+        self._eval_cache_valid = False
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._eval_cache_valid = False
+        return super().load_state_dict(*args, **kwargs)
+
+    def __init_weight(self):
+        # model/lgcn.py:70-76: one table, users first, N(0, 0.1^2)
+        self.all_embedding = nn.Embedding(self.num_users + self.num_items, self.latent_dim,
+                                          device=self.device)
+        nn.init.normal_(self.all_embedding.weight, std=0.1)
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, name: str) -> torch.Tensor:
+        t = self._bufs.get(name)
+        if t is None:
+            N, d, dev = self.num_users + self.num_items, self.latent_dim, self.all_embedding.weight.device
+            if name in ("Z0", "Z1"):
+                t = torch.empty((N, d), dtype=self.storage_dtype, device=dev)
+            elif name in ("ACC", "OUT"):
+                t = torch.empty((N, d), dtype=torch.float32, device=dev)
+            elif name == "G":
+                t = torch.zeros((N, d), dtype=torch.float32, device=dev)
+            elif name in ("cnt", "zero_cnt"):
+                t = torch.zeros(N, dtype=torch.int32, device=dev)
+            elif name == "loss_out":
+                t = torch.zeros(4, dtype=torch.float32, device=dev)
+            elif name == "work_counter":
+                t = torch.zeros(1, dtype=torch.int32, device=dev)
+            else:
+                raise KeyError(name)
+            self._bufs[name] = t
+        return t
+
+    def _work(self, batch: int) -> torch.Tensor:
+        t = self._bufs.get("work")
+        if t is None or t.numel() < 2 * batch:
+            t = torch.empty(2 * max(batch, 1), dtype=torch.float32, device=self.all_embedding.weight.device)
+            self._bufs["work"] = t
+        return t
+
+    def _zero_cnt(self) -> torch.Tensor:
+        return self._buf("zero_cnt")
+
+    def _reset_seed_buffers(self) -> None:
+        if not self._g_clean:
+            self._buf("G").zero_()
+            self._buf("cnt").zero_()
+            self._g_clean = True
+
+    # ------------------------------------------------------------- propagation
+    def _propagate_into(self, emb: torch.Tensor, out: torch.Tensor) -> None:
+        """out = (X0 + .. + XK)/(K+1), X0 = emb, X_{k+1} = A_hat X_k  (model/lgcn.py:78-86)."""
+        K, g = self.num_layers, self.graph
+        z = [self._buf("Z0"), self._buf("Z1")]
+        acc = self._buf("ACC")
+        for k in range(K):
+            last = k == K - 1
+            ops.propagate_layer(
+                g, emb if k == 0 else z[(k - 1) & 1], scale_src=(k == 0),
+                dst=None if last else z[k & 1],
+                acc_in=emb if k == 0 else acc, acc_out=out if last else acc,
+                acc_scale=1.0 / (K + 1) if last else 1.0)
+
+    def _horner_into(self, G: torch.Tensor, *, grad_mode: int, reg_coef: float, cnt: torch.Tensor,
+                     grad: Optional[torch.Tensor] = None, adam: Optional[dict] = None) -> None:
+        """H0 = G, H_{j+1} = G + A_hat H_j; result H_K/(K+1) + reg_coef*cnt*E goes to
+        `grad` (mode 1) or straight into Adam (mode 2)  (SURVEY §8 a-3)."""
+        K, g = self.num_layers, self.graph
+        z = [self._buf("Z0"), self._buf("Z1")]
+        w = self.all_embedding.weight.detach()
+        for j in range(K):
+            last = j == K - 1
+            kw = {}
+            if last:
+                kw = dict(grad_mode=grad_mode, inv_layers=1.0 / (K + 1), reg_coef=reg_coef, cnt=cnt, emb=w,
+                          grad=grad)
+                if adam is not None:
+                    kw.update(adam_m=adam["exp_avg"], adam_v=adam["exp_avg_sq"], adam_hp=adam["hp"],
+                              betas=adam["betas"], eps=adam["eps"], zero_base=K > 1)
+            ops.propagate_layer(g, G if j == 0 else z[(j - 1) & 1], scale_src=(j == 0),
+                                dst=None if last else z[j & 1], base=G, **kw)
+
+    def computer(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Propagated (users, items) embeddings — model/MF.py:178-210 naming."""
+        w = self.all_embedding.weight
+        if torch.is_grad_enabled() and w.requires_grad:
+            out = _PropagateFn.apply(w, self)
+        else:
+            out = self._buf("OUT")
+            if self.training or not self._eval_cache_valid:
+                self._propagate_into(w.detach(), out)
+                self._eval_cache_valid = not self.training
+        return out[: self.num_users], out[self.num_users:]
+
+    def forward(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """model/lgcn.py:78-86"""
+        return self.computer()
+
+    # ------------------------------------------------------------------ losses
+    def getEmbedding(self, users, pos_items, neg_items):
+        """model/lgcn.py:88-96"""
+        all_users, all_items = self.forward()
+        users, pos_items, neg_items = users.long(), pos_items.long(), neg_items.long()
+        return (all_users[users], all_items[pos_items], all_items[neg_items],
+                self.all_embedding(users), self.all_embedding(pos_items + self.num_users),
+                self.all_embedding(neg_items + self.num_users))
+
+    def bpr_loss(self, users, pos, neg):
+        """(loss, reg_loss) of model/lgcn.py:98-118, differentiable wrt all_embedding."""
+        users, pos, neg = self._ids(users), self._ids(pos), self._ids(neg)
+        return _BprFn.apply(self.all_embedding.weight, self, users, pos, neg)
+
+    def _ids(self, t) -> torch.Tensor:
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(t)
+        return t.to(device=self.all_embedding.weight.device, dtype=torch.int64).contiguous()
+
+    @torch.no_grad()
+    def stageOne(self, user, pos, neg) -> torch.Tensor:
+        """model/lgcn.py:127-133 as one fused step: zero_grad + bpr_loss +
+        decay*reg + backward + Adam.  Returns loss + decay*reg (0-dim tensor)."""
+        users, pos, neg = self._ids(user), self._ids(pos), self._ids(neg)
+        self._fused_step(users, pos, neg)
+        return self._buf("loss_out")[2].clone()
+
+    def _fused_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> None:
+        w = self.all_embedding.weight
+        B = users.numel()
+        group = self.optim.param_groups[0]
+        st = self.optim._init_state(w)
+        out = self._buf("OUT")
+        self._propagate_into(w.data, out)
+        self._reset_seed_buffers()
+        G, cnt = self._buf("G"), self._buf("cnt")
+        decay = float(self.config["decay"])
+        ops.bpr_fwd_bwd(out, w.data, users, pos, neg, self.num_users, decay, G, cnt, self._buf("loss_out"),
+                        self._work(B), self._buf("work_counter"))
+        ops.adam_tick(st["step"], st["hp"], group["lr"], group["betas"])
+        adam = dict(exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"], hp=st["hp"], betas=group["betas"],
+                    eps=group["eps"])
+        self._horner_into(G, grad_mode=2, reg_coef=decay / B, cnt=cnt, adam=adam)
+        if self.num_layers == 1:  # the single layer gathers from G, so it cannot clear it in flight
+            G.zero_()
+        self._eval_cache_valid = False
+
+    @torch.no_grad()
+    def OneEpoch(self, user, pos, neg) -> torch.Tensor:
+        """model/lgcn.py:135-151: contiguous mini-batches of bpr_batch_size, the
+        epoch loss is sum / (len // B + 1) (sic)."""
+        users, pos, neg = self._ids(user), self._ids(pos), self._ids(neg)
+        B = int(self.config["bpr_batch_size"])
+        total_batch = len(users) // B + 1
+        lo = self._buf("loss_out")
+        lo[3] = 0.0
+        for i in range(0, len(users), B):
+            self._fused_step(users[i:i + B], pos[i:i + B], neg[i:i + B])
+        return lo[3] / total_batch
+
+    # -------------------------------------------------------------------- eval
+    @torch.no_grad()
+    def getUsersRating(self, users) -> torch.Tensor:
+        """model/lgcn.py:120-125: dense raw scores [U_b, m] (no sigmoid).  Kept for
+        Trainer.test compatibility; reuses the cached propagation in eval mode.
+        The dense product is a plain library GEMM — the fused path is getUsersTopK."""
+        all_users, all_items = self.computer()
+        return torch.matmul(all_users[self._ids(users)], all_items.t())
+
+    @torch.no_grad()
+    def getUsersTopK(self, users, k: int, mask_train: bool = True, precision: Optional[str] = None):
+        """score -> mask train positives with -1024 -> top-k (ties: lowest id), fused
+        (model/lgcn.py:120-125 + trainer.py:132-138).  Returns (idx int32[U,k], val fp32[U,k])."""
+        all_users, all_items = self.computer()
+        rowptr, _, srt = self.dataset.pos_csr()
+        if not mask_train:
+            rowptr = torch.zeros_like(rowptr)
+        return ops.score_topk(all_users, all_items, self._ids(users), rowptr, srt, k,
+                              precision=precision or self.eval_precision)

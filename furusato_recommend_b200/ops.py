@@ -1,0 +1,200 @@
+"""Tensor-level wrappers over the C ABI (ctypes).  PyTorch is plumbing here:
+device memory, the current stream and dtype checks.  Every op runs the CUDA
+kernels of liblgcn_b200.so on the caller's current stream; CPU tensors are
+rejected (there is no fallback)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from .graph import CsrGraph
+
+MASK_VALUE = -float(1 << 10)  # reference trainer.py:137
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Optional[torch.Tensor], dtype, name: str, allow_none: bool = False) -> int:
+    if t is None:
+        if allow_none:
+            return 0
+        raise ValueError(f"{name} is required")
+    if not t.is_cuda:
+        raise _lib.LgcnLibraryError(f"{name} must be a CUDA tensor: the LightGCN hot path has no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise TypeError(f"unsupported storage dtype {t.dtype}")
+
+
+def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Optional[torch.Tensor] = None,
+                    base: Optional[torch.Tensor] = None, acc_in: Optional[torch.Tensor] = None,
+                    acc_out: Optional[torch.Tensor] = None, acc_scale: float = 1.0,
+                    grad_mode: int = 0, inv_layers: float = 1.0, reg_coef: float = 0.0,
+                    cnt: Optional[torch.Tensor] = None, emb: Optional[torch.Tensor] = None,
+                    grad: Optional[torch.Tensor] = None, adam_m: Optional[torch.Tensor] = None,
+                    adam_v: Optional[torch.Tensor] = None, adam_hp: Optional[torch.Tensor] = None,
+                    betas=(0.9, 0.999), eps: float = 1e-8, zero_base: bool = False) -> None:
+    """lgcn_propagate_layer: one normalised-adjacency SpMM + fused row epilogue."""
+    lib = _lib.load()
+    N, d = src.shape
+    if N != g.n_nodes:
+        raise ValueError(f"src has {N} rows, graph has {g.n_nodes} nodes")
+    a = _lib.LayerArgs()
+    a.d, a.src_dtype, a.scale_src = d, _dt(src), int(scale_src)
+    a.dst_dtype = _dt(dst) if dst is not None else _dt(src)
+    a.src = _chk(src, src.dtype, "src")
+    a.dst = _chk(dst, dst.dtype, "dst") if dst is not None else 0
+    a.base = _chk(base, torch.float32, "base", True)
+    a.acc_in = _chk(acc_in, torch.float32, "acc_in", True)
+    a.acc_out = _chk(acc_out, torch.float32, "acc_out", True)
+    a.acc_scale = acc_scale
+    a.grad_mode, a.inv_layers, a.reg_coef = grad_mode, inv_layers, reg_coef
+    a.cnt = _chk(cnt, torch.int32, "cnt", True)
+    a.emb = _chk(emb, torch.float32, "emb", True)
+    a.grad = _chk(grad, torch.float32, "grad", True)
+    a.adam_m = _chk(adam_m, torch.float32, "adam_m", True)
+    a.adam_v = _chk(adam_v, torch.float32, "adam_v", True)
+    a.adam_hp = _chk(adam_hp, torch.float32, "adam_hp", True)
+    a.beta1, a.beta2, a.eps = betas[0], betas[1], eps
+    a.zero_base = int(zero_base)
+    for t, nm in ((dst, "dst"), (base, "base"), (acc_in, "acc_in"), (acc_out, "acc_out"), (emb, "emb"),
+                  (grad, "grad"), (adam_m, "adam_m"), (adam_v, "adam_v")):
+        if t is not None and tuple(t.shape) != (N, d):
+            raise ValueError(f"{nm} must be [{N}, {d}], got {tuple(t.shape)}")
+    _lib.check(lib.lgcn_propagate_layer(C.byref(g.c_struct(d)), C.byref(a), _stream()), "lgcn_propagate_layer")
+
+
+def bpr_fwd_bwd(out: torch.Tensor, emb: torch.Tensor, users: torch.Tensor, pos: torch.Tensor,
+                neg: torch.Tensor, n_users: int, decay: float, G: torch.Tensor, cnt: torch.Tensor,
+                loss_out: torch.Tensor, work: torch.Tensor, work_counter: torch.Tensor,
+                loss_scale: float = 1.0) -> None:
+    lib = _lib.load()
+    B = users.numel()
+    N, d = out.shape
+    if work.numel() < 2 * B:
+        raise ValueError("work must hold 2*B floats")
+    _lib.check(lib.lgcn_bpr_fwd_bwd(
+        _chk(out, torch.float32, "out"), _chk(emb, torch.float32, "emb"),
+        _chk(users, torch.int64, "users"), _chk(pos, torch.int64, "pos"), _chk(neg, torch.int64, "neg"),
+        B, n_users, N, d, decay, loss_scale, _chk(G, torch.float32, "G"), _chk(cnt, torch.int32, "cnt"),
+        _chk(loss_out, torch.float32, "loss_out"), _chk(work, torch.float32, "work"),
+        _chk(work_counter, torch.int32, "work_counter"), _stream()), "lgcn_bpr_fwd_bwd")
+
+
+def adam_tick(step: torch.Tensor, hp: torch.Tensor, lr: float, betas=(0.9, 0.999)) -> None:
+    lib = _lib.load()
+    _lib.check(lib.lgcn_adam_tick(_chk(step, torch.int64, "step"), _chk(hp, torch.float32, "adam_hp"),
+                                  lr, betas[0], betas[1], _stream()), "lgcn_adam_tick")
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, hp: torch.Tensor,
+              betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+    lib = _lib.load()
+    _lib.check(lib.lgcn_adam_step(_chk(param, torch.float32, "param"), _chk(grad, torch.float32, "grad"),
+                                  _chk(m, torch.float32, "m"), _chk(v, torch.float32, "v"), param.numel(),
+                                  _chk(hp, torch.float32, "adam_hp"), betas[0], betas[1], eps, _stream()),
+               "lgcn_adam_step")
+
+
+def uniform_sample(pos_rowptr: torch.Tensor, pos_file: torch.Tensor, pos_sorted: torch.Tensor,
+                   n_users: int, m_items: int, count: int, seed: int, epoch: int, first: int = 0):
+    """Returns (triples int64[count,3], valid uint8[count]) — not yet compacted."""
+    lib = _lib.load()
+    dev = pos_rowptr.device
+    triples = torch.empty((count, 3), dtype=torch.int64, device=dev)
+    valid = torch.empty(count, dtype=torch.uint8, device=dev)
+    _lib.check(lib.lgcn_uniform_sample(
+        _chk(pos_rowptr, torch.int64, "pos_rowptr"), _chk(pos_file, torch.int32, "pos_file"),
+        _chk(pos_sorted, torch.int32, "pos_sorted"), n_users, m_items, first, count,
+        seed & 0xFFFFFFFFFFFFFFFF, epoch & 0xFFFFFFFF, triples.data_ptr(), valid.data_ptr(), _stream()),
+        "lgcn_uniform_sample")
+    return triples, valid
+
+
+def compact_triples(triples: torch.Tensor, valid: torch.Tensor) -> torch.Tensor:
+    """Order-preserving compaction; one host sync to learn the row count."""
+    lib = _lib.load()
+    count = valid.numel()
+    dev = triples.device
+    out = torch.empty_like(triples)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    scratch = torch.empty((count + 1023) // 1024 + 1, dtype=torch.int64, device=dev)
+    _lib.check(lib.lgcn_compact_triples(_chk(triples, torch.int64, "triples"), _chk(valid, torch.uint8, "valid"),
+                                        count, out.data_ptr(), n_out.data_ptr(), scratch.data_ptr(), _stream()),
+               "lgcn_compact_triples")
+    return out[: int(n_out.item())]
+
+
+def score_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, user_ids: torch.Tensor,
+               pos_rowptr: torch.Tensor, pos_sorted: torch.Tensor, k: int,
+               mask_value: float = MASK_VALUE, precision: str = "fp32"):
+    """Fused score + mask + top-k.  Returns (idx int32[U,k], val fp32[U,k])."""
+    lib = _lib.load()
+    U = user_ids.numel()
+    m, d = item_emb.shape
+    dev = item_emb.device
+    idx = torch.empty((U, k), dtype=torch.int32, device=dev)
+    val = torch.empty((U, k), dtype=torch.float32, device=dev)
+    prec = {"fp32": _lib.F32, "bf16": _lib.BF16}[precision]
+    _lib.check(lib.lgcn_score_topk(
+        _chk(user_emb, torch.float32, "user_emb"), _chk(item_emb, torch.float32, "item_emb"),
+        _chk(user_ids, torch.int64, "user_ids"), U, m, d, _chk(pos_rowptr, torch.int64, "pos_rowptr"),
+        _chk(pos_sorted, torch.int32, "pos_sorted"), k, mask_value, prec, idx.data_ptr(), val.data_ptr(),
+        _stream()), "lgcn_score_topk")
+    return idx, val
+
+
+def score_dense_f32(user_emb: torch.Tensor, item_emb: torch.Tensor, user_ids: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    U = user_ids.numel()
+    m, d = item_emb.shape
+    out = torch.empty((U, m), dtype=torch.float32, device=item_emb.device)
+    _lib.check(lib.lgcn_score_dense_f32(_chk(user_emb, torch.float32, "user_emb"),
+                                        _chk(item_emb, torch.float32, "item_emb"),
+                                        _chk(user_ids, torch.int64, "user_ids"), U, m, d, out.data_ptr(),
+                                        _stream()), "lgcn_score_dense_f32")
+    return out
+
+
+def rank_metrics(topk: torch.Tensor, user_ids: torch.Tensor, test_rowptr: torch.Tensor,
+                 test_sorted: torch.Tensor, ks: Sequence[int], sums: Optional[torch.Tensor] = None,
+                 want_hits: bool = False):
+    """Adds the recall/precision/hr/ndcg SUMS of this batch into sums[4, len(ks)] (fp64)."""
+    lib = _lib.load()
+    U, k = topk.shape
+    dev = topk.device
+    ks = [int(x) for x in ks]
+    order = sorted(range(len(ks)), key=lambda i: ks[i])
+    ks_sorted = [ks[i] for i in order]
+    tmp = torch.zeros((4, len(ks)), dtype=torch.float64, device=dev)
+    hits = torch.empty((U, k), dtype=torch.uint8, device=dev) if want_hits else None
+    arr = (C.c_int32 * len(ks))(*ks_sorted)
+    _lib.check(lib.lgcn_rank_metrics(_chk(topk, torch.int32, "topk"), U, k, _chk(user_ids, torch.int64, "user_ids"),
+                                     _chk(test_rowptr, torch.int64, "test_rowptr"),
+                                     _chk(test_sorted, torch.int32, "test_sorted"), arr, len(ks),
+                                     tmp.data_ptr(), hits.data_ptr() if hits is not None else 0, _stream()),
+               "lgcn_rank_metrics")
+    inv = torch.empty(len(ks), dtype=torch.long)
+    for pos_sorted_i, orig_i in enumerate(order):
+        inv[orig_i] = pos_sorted_i
+    tmp = tmp[:, inv.to(dev)]
+    if sums is None:
+        sums = tmp
+    else:
+        sums += tmp
+    return (sums, hits) if want_hits else sums

@@ -1,0 +1,206 @@
+/* lgcn_b200.h — C ABI of the B200-native LightGCN hot path (liblgcn_b200.so).
+ *
+ * The reference (HiromasaYamanishi/furusato_recommend) is pure Python and has no
+ * FFI boundary: its seam is the duck-typed model/sampler/dataset API.  Each entry
+ * point below replaces the torch / PyG / numpy call sites named in its comment
+ * (paths relative to the reference root).  The Python host layer in
+ * furusato_recommend_b200/ binds these with ctypes and keeps the reference's
+ * method names (LightGCN.computer/forward/bpr_loss/getUsersRating/stageOne,
+ * UniformSample, Loader.getSparseGraph).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless it says HOST;
+ *     outputs are pre-allocated by the caller; no allocation happens inside;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     stateless and re-entrant; it can be captured into a CUDA graph;
+ *   - return value: 0 = ok, > 0 = a cudaError_t, < 0 = LGCN_ERR_*; the message is
+ *     available from lgcn_last_error() (thread-local).  Nothing throws.
+ *   - embedding rows are row-major [N, d] with users first, then items
+ *     (model/lgcn.py:71-74), 16-byte aligned, d in {32, 64, 128} (bf16: also 256).
+ */
+#ifndef LGCN_B200_H
+#define LGCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGCN_ABI_VERSION 1
+
+#define LGCN_ERR_INVALID_ARG (-1)
+#define LGCN_ERR_UNSUPPORTED (-2)
+
+#define LGCN_F32 0
+#define LGCN_BF16 1
+
+/* rows with more than LGCN_HUB_DEG edges are split into CTA-wide segments of at
+ * most LGCN_SEG_EDGES edges (host side builds the lists, see graph.py) */
+#define LGCN_HUB_DEG 256
+#define LGCN_SEG_EDGES 1024
+
+typedef void* lgcn_stream_t; /* cudaStream_t */
+
+int lgcn_abi_version(void);
+const char* lgcn_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Graph: CSR of the bipartite adjacency A = [[0,R],[R^T,0]] WITHOUT values.
+ * Replaces the COO FloatTensor of Loader.getSparseGraph (dataloader.py:215-258):
+ * the normalisation D^-1/2 A D^-1/2 is folded into `dinv` (dataloader.py:236-238),
+ * multi-edges are repeated column entries (csr_matrix sums duplicates, :164).
+ * ------------------------------------------------------------------------ */
+typedef struct lgcn_graph {
+  int64_t n_nodes;           /* N = n_users + m_items                          */
+  int64_t nnz;               /* directed entries (= 2 * train interactions)    */
+  const int64_t* rowptr;     /* [N+1]                                          */
+  const int32_t* col;        /* [nnz] neighbour node ids, sorted inside a row  */
+  const float* dinv;         /* [N] deg^-1/2 (fp32), 0 where deg == 0          */
+  /* work decomposition (degree-descending so long rows start first) */
+  const int32_t* light_rows; /* [n_light] rows with deg <= LGCN_HUB_DEG        */
+  int64_t n_light;
+  const int32_t* seg_row;    /* [n_seg] hub row of each CTA segment            */
+  const int64_t* seg_begin;  /* [n_seg] first edge                             */
+  const int32_t* seg_len;    /* [n_seg] edges in the segment (<= SEG_EDGES)    */
+  const int32_t* seg_hub;    /* [n_seg] index into the hub arrays              */
+  int64_t n_seg;
+  const int32_t* hub_seg0;   /* [n_hub] first segment of the hub               */
+  const int32_t* hub_nseg;   /* [n_hub] number of segments                     */
+  int32_t* hub_counter;      /* [n_hub] zero-initialised; self-resetting       */
+  int64_t n_hub;
+  float* partial;            /* [n_seg * d] fp32 scratch for multi-segment hubs */
+} lgcn_graph_t;
+
+/* ------------------------------------------------------------------------
+ * One propagation layer  s_i = sum_{j in N(i)} w_j * SRC[j]  fused with a row
+ * epilogue.  Replaces torch.sparse.mm(G, all_emb) (model/MF.py:200,204) ==
+ * LGConv()(x, edge_index) (model/lgcn.py:82), the running layer sum
+ * (model/lgcn.py:83-84, model/MF.py:206-208), their autograd transposes
+ * (A_hat is symmetric, so backward is the same kernel in Horner form) and,
+ * optionally, optim.Adam.step() (model/lgcn.py:63,132).
+ *
+ *   w_j = dinv[j] if scale_src else 1 (then SRC must already hold dinv (.) X)
+ *   x_i = dinv[i] * s_i                       (= (A_hat X)[i])
+ *   t_i = base ? base[i] + x_i : x_i          (backward: base = G)
+ *   if dst:      dst[i]     = dinv[i] * t_i   (pre-scaled source of the next layer)
+ *   if acc_out:  acc_out[i] = (acc_in[i] + x_i) * acc_scale   (running layer sum;
+ *                last layer: acc_scale = 1/(K+1) gives light_out)
+ *   if grad_mode: g_i = t_i * inv_layers + reg_coef * cnt[i] * emb[i]
+ *        1: grad[i] = g_i
+ *        2: Adam(emb[i], m[i], v[i], g_i) with the step sizes in adam_hp, then
+ *           cnt[i] = 0 and, if zero_base, base[i] = 0 (so the next step starts
+ *           clean; zero_base is illegal when src == base, i.e. K == 1)
+ * ------------------------------------------------------------------------ */
+typedef struct lgcn_layer_args {
+  int d;               /* embedding width                                       */
+  int src_dtype;       /* LGCN_F32 | LGCN_BF16                                  */
+  int dst_dtype;       /* LGCN_F32 | LGCN_BF16                                  */
+  int scale_src;       /* 1: multiply neighbours by dinv[j] on the fly (f32 src) */
+  const void* src;     /* [N,d]                                                 */
+  void* dst;           /* [N,d] or NULL                                         */
+  const float* base;   /* [N,d] fp32 or NULL                                    */
+  const float* acc_in; /* [N,d] fp32 or NULL                                    */
+  float* acc_out;      /* [N,d] fp32 or NULL (may alias acc_in)                 */
+  float acc_scale;
+  int grad_mode;       /* 0 | 1 | 2                                             */
+  float inv_layers;    /* 1/(K+1)                                               */
+  float reg_coef;      /* decay / B                                             */
+  int32_t* cnt;        /* [N] occurrences of row i in the batch (bpr kernel)    */
+  float* emb;          /* [N,d] fp32 embedding table E                          */
+  float* grad;         /* [N,d] fp32 (grad_mode 1)                              */
+  float* adam_m;       /* [N,d] fp32 (grad_mode 2)                              */
+  float* adam_v;       /* [N,d] fp32 (grad_mode 2)                              */
+  const float* adam_hp;/* device float[2]: {lr/bc1, sqrt(bc2)} (lgcn_adam_tick)  */
+  double beta1, beta2, eps;
+  int zero_base;       /* grad_mode 2: clear base[i] after use                  */
+} lgcn_layer_args_t;
+
+int lgcn_propagate_layer(const lgcn_graph_t* g /*HOST*/, const lgcn_layer_args_t* a /*HOST*/,
+                         lgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Fused BPR forward + backward seed.  Replaces getEmbedding + bpr_loss
+ * (model/lgcn.py:88-118) and the autograd scatter of loss.backward()
+ * (model/lgcn.py:131):
+ *   x_b = <out[u_b], out[n+neg_b]> - <out[u_b], out[n+pos_b]>
+ *   loss_out[0] = mean_b softplus(x_b)  (torch threshold 20)
+ *   loss_out[1] = 0.5 * sum_b(|E[u_b]|^2+|E[n+pos_b]|^2+|E[n+neg_b]|^2) / B
+ *   loss_out[2] = loss_out[0] + decay * loss_out[1]
+ *   loss_out[3] += loss_out[2]          (running epoch sum, model/lgcn.py:149)
+ *   G[u_b] += s_b (out[n+neg_b] - out[n+pos_b]);  G[n+pos_b] -= s_b out[u_b];
+ *   G[n+neg_b] += s_b out[u_b],  s_b = loss_scale * sigmoid(x_b) / B
+ *   cnt[row]  += 1 for each of the 3 rows of every sample
+ * G and cnt must be zero on entry.  work: float[2*B] + int32[1] (zeroed once).
+ * ------------------------------------------------------------------------ */
+int lgcn_bpr_fwd_bwd(const float* out, const float* emb, const int64_t* users, const int64_t* pos,
+                     const int64_t* neg, int64_t batch, int64_t n_users, int64_t n_nodes, int d,
+                     float decay, float loss_scale, float* G, int32_t* cnt, float* loss_out,
+                     float* work, int32_t* work_counter, lgcn_stream_t stream);
+
+/* Adam bookkeeping: ++(*step) and adam_hp = {lr / (1-beta1^t), sqrt(1-beta2^t)}
+ * in double precision like torch.optim.Adam's Python scalars. */
+int lgcn_adam_tick(int64_t* step, float* adam_hp, double lr, double beta1, double beta2,
+                   lgcn_stream_t stream);
+
+/* Dense Adam on a [numel] fp32 tensor given its gradient — optim.Adam.step()
+ * (model/lgcn.py:132) for callers that bring their own gradient (autograd path). */
+int lgcn_adam_step(float* param, const float* grad, float* m, float* v, int64_t numel,
+                   const float* adam_hp, double beta1, double beta2, double eps,
+                   lgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Uniform negative sampler.  Replaces negative_sample.UniformSample
+ * (negative_sample.py:98-134).  Sample i draws word j%4 of
+ * Philox4x32-10(key=(seed_lo,seed_hi), ctr=(i_lo,i_hi,j/4,epoch)); draw 0 picks
+ * the user (mulhi32(r,n_users)), draw 1 the positive from the FILE-ORDER list
+ * (:119-120), draws 2.. the first item not contained in the user's positives
+ * (:121-126, membership by binary search in the sorted copy).  Users with an
+ * empty list get valid[i]=0 (:116-117).  Samples [first, first+count) are drawn
+ * (a shard is a counter offset); triples: int64[count,3].
+ * ------------------------------------------------------------------------ */
+int lgcn_uniform_sample(const int64_t* pos_rowptr, const int32_t* pos_file, const int32_t* pos_sorted,
+                        int64_t n_users, int64_t m_items, int64_t first, int64_t count,
+                        uint64_t seed, uint32_t epoch, int64_t* triples, uint8_t* valid,
+                        lgcn_stream_t stream);
+
+/* Order-preserving compaction of the valid triples (np.array(S), :134).
+ * scratch: int64[ceil(count/1024) + 1]; n_out: device int64[1]. */
+int lgcn_compact_triples(const int64_t* triples, const uint8_t* valid, int64_t count,
+                         int64_t* out, int64_t* n_out, int64_t* scratch, lgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Full-rank scoring fused with train-positive masking and top-k.  Replaces
+ * getUsersRating's matmul (model/lgcn.py:124), the exclude-list index_put of
+ * -(1<<10) (trainer.py:132-137) and torch.topk (trainer.py:138); ties broken by
+ * lowest item id.  The [U,m] score matrix is never written.
+ *   user_emb/item_emb: propagated embeddings (light_out halves), fp32 [*,d]
+ *   user_ids: int64[n_eval] rows of user_emb to score
+ *   precision: LGCN_F32 exact fp32 FMA scores | LGCN_BF16 tcgen05 tensor cores
+ * out_idx int32[n_eval,k] (sorted by score desc, id asc), out_val fp32[n_eval,k].
+ * ------------------------------------------------------------------------ */
+int lgcn_score_topk(const float* user_emb, const float* item_emb, const int64_t* user_ids,
+                    int64_t n_eval, int64_t m_items, int d, const int64_t* pos_rowptr,
+                    const int32_t* pos_sorted, int k, float mask_value, int precision,
+                    int32_t* out_idx, float* out_val, lgcn_stream_t stream);
+
+/* Debug/test aid: the dense fp32 score block the F32 top-k path selects from
+ * (same FMA order), scores[n_eval, m_items].  Small shapes only. */
+int lgcn_score_dense_f32(const float* user_emb, const float* item_emb, const int64_t* user_ids,
+                         int64_t n_eval, int64_t m_items, int d, float* scores,
+                         lgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Ranking metrics on device.  Replaces utils.getLabel (utils.py:40-48),
+ * RecallPrecision_ATk (metric.py:60-72) and NDCGatK_r (metric.py:84-103):
+ * sums[4][n_ks] (double) += recall, precision, hr, ndcg sums over the users.
+ * ------------------------------------------------------------------------ */
+int lgcn_rank_metrics(const int32_t* topk, int64_t n_eval, int k, const int64_t* user_ids,
+                      const int64_t* test_rowptr, const int32_t* test_sorted,
+                      const int32_t* ks /*HOST, ascending*/, int n_ks, double* sums, uint8_t* hits /* [n_eval,k] or NULL */,
+                      lgcn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGCN_B200_H */
