@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--storage", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     return ap.parse_args()
 
 
@@ -253,33 +254,62 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(); model.computer(); p1.record()
         rp, srt = ds.test_csr()
-        tr.test()  # warm-up
-        reps = 3
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a0.record()
-        for _ in range(reps):
+        peak_tf = measured_peaks()[1]
+
+        def eval_pass(precision):
             sums = torch.zeros((4, 2), dtype=torch.float64, device=dev)
-            for s0 in range(0, len(ev_users), 10000):
+            for s0 in range(0, len(ev_users), 10000):          # test_u_batch_size (parse.py:24)
                 bu = ev_users[s0:s0 + 10000]
-                idx, _ = model.getUsersTopK(bu, 20)
+                idx, _ = model.getUsersTopK(bu, 20, precision=precision)
                 lmetric.batch_metric_sums(idx, bu, rp, srt, (10, 20), sums)
-        a1.record()
-        torch.cuda.synchronize()
-        t_eval = a0.elapsed_time(a1) / 1e3 / reps
-        hosts = torch.from_numpy(ds.test_users()).pin_memory()
+            return sums
+
+        def timed(fn, reps):
+            fn(); torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                fn()
+            a1.record(); torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / 1e3 / reps
+
+        t_tc = timed(lambda: eval_pass("bf16"), 5)
+        t_f32 = timed(lambda: eval_pass("fp32"), 3)
+        model.eval_precision = "bf16"
+        tr.test()
         w0 = time.perf_counter()
         res = tr.test()  # public API: host user ids in, metric dict out
         torch.cuda.synchronize()
         t_eval_e2e = time.perf_counter() - w0
-        peak_tf = measured_peaks()[1]
+        model.eval_precision = "fp32"
+        res32 = tr.test()
         flops = 2.0 * len(ev_users) * m * d
         eval_info = {"metric": "full-rank top-20 eval users/sec (score+mask+top-k+metrics)",
-                     "value": len(ev_users) / t_eval, "unit": "users/s", "users": int(len(ev_users)), "items": m,
-                     "precision": model.eval_precision, "propagation_ms": p0.elapsed_time(p1),
+                     "value": len(ev_users) / t_tc, "unit": "users/s", "users": int(len(ev_users)), "items": m,
+                     "precision": "bf16 tcgen05 (fp32 accumulate)", "propagation_ms": p0.elapsed_time(p1),
                      "e2e": {"value": len(ev_users) / t_eval_e2e, "unit": "users/s"},
-                     "tflops": flops / t_eval / 1e12, "tensor_peak_tflops": peak_tf,
-                     "recall@20": float(res["recall"][1]), "ndcg@20": float(res["ndcg"][1])}
+                     "tflops": flops / t_tc / 1e12, "tensor_peak_tflops": peak_tf,
+                     "fp32_exact_value": len(ev_users) / t_f32,
+                     "recall@20": float(res["recall"][1]), "ndcg@20": float(res["ndcg"][1]),
+                     "recall@20_fp32": float(res32["recall"][1]), "ndcg@20_fp32": float(res32["ndcg"][1])}
+        # cfg-5-shaped sweep: the tensor-pipe figure is only meaningful at m = 2M items
+        if not args.no_sweep:
+            U5, m5 = 148 * 128 * 4, 2_000_000
+            g5 = torch.Generator(device=dev).manual_seed(5)
+            ue5 = torch.randn(U5, d, generator=g5, device=dev) * 0.1
+            ie5 = torch.randn(m5, d, generator=g5, device=dev) * 0.1
+            ids5 = torch.arange(U5, device=dev)
+            npos = 50
+            rp5 = torch.arange(U5 + 1, device=dev, dtype=torch.int64) * npos
+            pos5 = torch.sort(torch.randint(0, m5, (U5, npos), generator=g5, device=dev, dtype=torch.int32), dim=1)[0]
+            pos5 = pos5.reshape(-1).contiguous()
+            t5 = timed(lambda: ops.score_topk(ue5, ie5, ids5, rp5, pos5, 20, precision="bf16"), 3)
+            fl5 = 2.0 * U5 * m5 * d
+            eval_info["sweep_cfg5"] = {"users": U5, "items": m5, "d": d, "k": 20, "masked_per_user": npos,
+                                       "value": U5 / t5, "unit": "users/s", "ms": t5 * 1e3,
+                                       "tflops": fl5 / t5 / 1e12, "frac_of_tensor_peak": fl5 / t5 / 1e12 / peak_tf,
+                                       "includes": "fp32->bf16 operand packing of both tables + score + mask + top-k"}
+            del ue5, ie5, pos5
         model.train()
 
     # ---- max over ranks ----

@@ -23,7 +23,9 @@ namespace lgcn {
 int score_topk_tc(const float* user_emb, const float* item_emb, const int64_t* user_ids,
                   int64_t n_eval, int64_t m_items, int d, const int64_t* pos_rowptr,
                   const int32_t* pos_sorted, int k, float mask_value, int32_t* out_idx,
-                  float* out_val, cudaStream_t st);
+                  float* out_val, float* dense, void* workspace, size_t workspace_bytes,
+                  cudaStream_t st);
+size_t score_topk_tc_workspace(int64_t n_eval, int64_t m_items, int d);
 
 constexpr int kTU = 64;    // users per CTA
 constexpr int kTI = 128;   // items per tile
@@ -214,22 +216,25 @@ static int launch_f32(const float* user_emb, const float* item_emb, const int64_
 
 using namespace lgcn;
 
-extern "C" int lgcn_score_topk(const float* user_emb, const float* item_emb,
-                               const int64_t* user_ids, int64_t n_eval, int64_t m_items, int d,
-                               const int64_t* pos_rowptr, const int32_t* pos_sorted, int k,
-                               float mask_value, int precision, int32_t* out_idx, float* out_val,
-                               lgcn_stream_t stream) {
+static int score_topk_impl(const float* user_emb, const float* item_emb, const int64_t* user_ids,
+                           int64_t n_eval, int64_t m_items, int d, const int64_t* pos_rowptr,
+                           const int32_t* pos_sorted, int k, float mask_value, int precision,
+                           int32_t* out_idx, float* out_val, float* dense, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st) {
   LGCN_CHECK_ARG(user_emb && item_emb && user_ids && pos_rowptr && pos_sorted && out_idx && out_val,
                  "null pointer argument");
   LGCN_CHECK_ARG(n_eval >= 0 && n_eval < 0x7fffffffLL, "n_eval out of range");
   LGCN_CHECK_ARG(m_items > 0 && m_items < 0x7fffffffLL, "m_items out of range");
   LGCN_CHECK_ARG(k >= 1 && k <= 128 && k <= m_items, "k must be in [1, min(128, m_items)]");
   if (n_eval == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
   if (precision == LGCN_BF16)
     return score_topk_tc(user_emb, item_emb, user_ids, n_eval, m_items, d, pos_rowptr, pos_sorted,
-                         k, mask_value, out_idx, out_val, st);
+                         k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes, st);
   LGCN_CHECK_ARG(precision == LGCN_F32, "precision must be LGCN_F32 or LGCN_BF16");
+  if (dense != nullptr) {
+    const int rc = lgcn_score_dense_f32(user_emb, item_emb, user_ids, n_eval, m_items, d, dense, st);
+    if (rc != 0) return rc;
+  }
   switch (d) {
     case 32: return launch_f32<32>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, st);
     case 64: return launch_f32<64>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, st);
@@ -238,6 +243,34 @@ extern "C" int lgcn_score_topk(const float* user_emb, const float* item_emb,
       set_last_error("unsupported embedding width d=%d (supported: 32, 64, 128)", d);
       return LGCN_ERR_UNSUPPORTED;
   }
+}
+
+extern "C" int64_t lgcn_score_topk_workspace_bytes(int64_t n_eval, int64_t m_items, int d,
+                                                   int precision) {
+  if (precision != LGCN_BF16 || n_eval <= 0 || m_items <= 0) return 0;
+  return (int64_t)score_topk_tc_workspace(n_eval, m_items, d);
+}
+
+extern "C" int lgcn_score_topk(const float* user_emb, const float* item_emb,
+                               const int64_t* user_ids, int64_t n_eval, int64_t m_items, int d,
+                               const int64_t* pos_rowptr, const int32_t* pos_sorted, int k,
+                               float mask_value, int precision, int32_t* out_idx, float* out_val,
+                               void* workspace, int64_t workspace_bytes, lgcn_stream_t stream) {
+  return score_topk_impl(user_emb, item_emb, user_ids, n_eval, m_items, d, pos_rowptr, pos_sorted, k,
+                         mask_value, precision, out_idx, out_val, nullptr, workspace,
+                         (size_t)(workspace_bytes < 0 ? 0 : workspace_bytes), (cudaStream_t)stream);
+}
+
+extern "C" int lgcn_score_topk_debug(const float* user_emb, const float* item_emb,
+                                     const int64_t* user_ids, int64_t n_eval, int64_t m_items, int d,
+                                     const int64_t* pos_rowptr, const int32_t* pos_sorted, int k,
+                                     float mask_value, int precision, int32_t* out_idx,
+                                     float* out_val, void* workspace, int64_t workspace_bytes,
+                                     float* dense_scores, lgcn_stream_t stream) {
+  LGCN_CHECK_ARG(dense_scores != nullptr, "dense_scores is null");
+  return score_topk_impl(user_emb, item_emb, user_ids, n_eval, m_items, d, pos_rowptr, pos_sorted, k,
+                         mask_value, precision, out_idx, out_val, dense_scores, workspace,
+                         (size_t)(workspace_bytes < 0 ? 0 : workspace_bytes), (cudaStream_t)stream);
 }
 
 extern "C" int lgcn_score_dense_f32(const float* user_emb, const float* item_emb,

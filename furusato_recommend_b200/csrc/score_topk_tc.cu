@@ -1,13 +1,506 @@
-// Tensor-core (tcgen05 / TMEM) full-rank scoring + top-k.  Placeholder until the
-// UMMA kernel lands: it reports LGCN_ERR_UNSUPPORTED, it never falls back.
+// Tensor-core full-rank scoring + masked top-k (precision = LGCN_BF16).
+//
+// Replaces getUsersRating's matmul (reference model/lgcn.py:124), the -(1<<10)
+// exclude-list index_put (trainer.py:132-137) and torch.topk (trainer.py:138).
+// The [U, m] score matrix only ever exists as 128 x TN fp32 accumulator tiles in
+// tensor memory.
+//
+// Structure (one CTA = 128 users, sweeps every item tile; sm_100a only):
+//   pack kernels   fp32 rows -> bf16 in the UMMA canonical K-major / no-swizzle
+//                  layout, one contiguous block per tile: [k-chunk(16 B)][row],
+//                  i.e. 8x16 B core matrices, SBO = 128 B, LBO = rows*16 B.
+//   warp 0         producer: one cp.async.bulk per tile (16/32 KB) -> smem ring,
+//                  completion on an mbarrier (expect_tx).
+//   warp 1         one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//                  (M=128, N=TN, K=16) d/16 times per tile into one of two TMEM
+//                  accumulator stages; tcgen05.commit frees the smem stage and
+//                  publishes the accumulator.
+//   warp 2         allocates / frees the 2*TN TMEM columns.
+//   warps 4..      epilogue: thread == TMEM lane == user row.  tcgen05.ld 32
+//                  columns at a time; a max-tree against the row's running
+//                  threshold rejects almost every chunk in ~1 op per score;
+//                  survivors are checked against the user's train positives
+//                  (binary search) and appended to a per-row shared-memory
+//                  buffer that is compacted warp-synchronously to the sorted
+//                  top-k.  Two epilogue groups take alternate accumulator stages
+//                  and are merged at the end (k <= 24); one group for larger k.
+// Ties: items arrive in ascending id inside a thread, filters are strict, the
+// final merge orders by (score desc, id asc) => lowest id wins, as in the fp32 path.
 #include "common.cuh"
 
 namespace lgcn {
+namespace tc {
 
-int score_topk_tc(const float*, const float*, const int64_t*, int64_t, int64_t, int, const int64_t*,
-                  const int32_t*, int, float, int32_t*, float*, cudaStream_t) {
-  set_last_error("precision LGCN_BF16 (tcgen05 path) is not built yet");
-  return LGCN_ERR_UNSUPPORTED;
+constexpr int kUM = 128;      // users per CTA == UMMA M
+constexpr int kFrontWarps = 4;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100 "version 1").
+//   bits [0,14)  start address >> 4        bits [16,30) leading (K) byte offset >> 4
+//   bits [32,46) stride (M/N) byte offset >> 4   bits [46,48) version = 1   [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- packing
+// dst tile t: [c = 0..D/8)[r = 0..R) 16-byte vectors = rows t*R+r, elements 8c..8c+7 (bf16)
+__global__ void __launch_bounds__(256)
+pack_bf16_kernel(const float* __restrict__ src, const int64_t* __restrict__ ids, int64_t n_rows, int D,
+                 int R, int64_t n_tiles, uint4* __restrict__ dst) {
+  const int cpr = D / 8;
+  const int64_t total = n_tiles * R * cpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpr);
+    const int64_t row = i / cpr;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (row < n_rows) {
+      const int64_t srow = ids ? ids[row] : row;
+      const float4 a = ld_f4(src + srow * D + 8 * c);
+      const float4 b = ld_f4(src + srow * D + 8 * c + 4);
+      o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+      o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    }
+    const int64_t t = row / R;
+    const int r = (int)(row % R);
+    dst[(t * cpr + c) * R + r] = o;
+  }
+}
+
+// ---------------------------------------------------------------- selection
+struct Sel {
+  float thr;   // current k-th best value of this thread's list (-inf until k entries exist)
+  int cnt;     // entries in the buffer
+  int sorted;  // entries [0, sorted) are ordered by (value desc, id asc)
+};
+
+__device__ __forceinline__ bool pos_contains(const int32_t* __restrict__ a, int n, int32_t x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && __ldg(a + lo) == x;
+}
+
+// Fold the unsorted tail [sorted, cnt) into the sorted top-k prefix.  New entries carry
+// larger ids than everything already held, so on equal value they go AFTER (strict <).
+__device__ __noinline__ Sel sel_compact(Sel s, float* cval, int* cidx, int NT, int k) {
+  for (int e = s.sorted; e < s.cnt; ++e) {
+    const float v = cval[e * NT];
+    const int id = cidx[e * NT];
+    int p;
+    if (s.sorted < k) {
+      p = s.sorted++;
+    } else {
+      if (!(v > cval[(k - 1) * NT])) continue;
+      p = k - 1;
+    }
+    while (p > 0 && cval[(p - 1) * NT] < v) {
+      cval[p * NT] = cval[(p - 1) * NT];
+      cidx[p * NT] = cidx[(p - 1) * NT];
+      --p;
+    }
+    cval[p * NT] = v;
+    cidx[p * NT] = id;
+  }
+  s.cnt = s.sorted;
+  s.thr = s.sorted == k ? cval[(k - 1) * NT] : -INFINITY;
+  return s;
+}
+
+__device__ __noinline__ Sel sel_append(Sel s, float raw, int item, const int32_t* pos, int npos,
+                                       float mask_value, float* cval, int* cidx, int NT, int cap, int k) {
+  const float v = pos_contains(pos, npos, item) ? mask_value : raw;  // trainer.py:137
+  if (!(v > s.thr)) return s;
+  if (s.cnt == cap) {  // rare (only while the threshold is still -inf): keep the buffer bounded
+    s = sel_compact(s, cval, cidx, NT, k);
+    if (!(v > s.thr)) return s;
+  }
+  cval[s.cnt * NT] = v;
+  cidx[s.cnt * NT] = item;
+  ++s.cnt;
+  return s;
+}
+
+__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
+  float m[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m[i] = fmaxf(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[2 * i], m[2 * i + 1]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m[i] = fmaxf(m[2 * i], m[2 * i + 1]);
+  return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+}
+
+struct Params {
+  const uint4* a_packed;   // user tiles, [n_utiles][D/8][128]
+  const uint4* b_packed;   // item tiles, [n_itiles][D/8][TN]
+  const int64_t* user_ids;
+  int n_eval, m_items;
+  const int64_t* pos_rowptr;
+  const int32_t* pos_sorted;
+  int k, cap, stages;
+  float mask_value;
+  int32_t* out_idx;
+  float* out_val;
+  float* dense;            // optional [n_eval, m_items] dump of the accumulators (tests)
+};
+
+template <int D, int TN, int GROUPS>
+__global__ void __launch_bounds__((kFrontWarps + 4 * GROUPS) * 32, 1)
+score_topk_tc_kernel(const Params p) {
+  constexpr int NT = GROUPS * 128;              // epilogue threads
+  constexpr uint32_t kABytes = kUM * D * 2;
+  constexpr uint32_t kBBytes = TN * D * 2;
+  constexpr int kKSteps = D / 16;
+  constexpr uint32_t kIdesc = make_idesc(kUM, TN);
+  constexpr int kMaxStages = 8;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sA = smem;
+  unsigned char* sB = sA + kABytes;
+  float* cval = reinterpret_cast<float*>(sB + (size_t)p.stages * kBBytes);
+  int* cidx = reinterpret_cast<int*>(cval + (size_t)p.cap * NT);
+  int* ccnt = cidx + (size_t)p.cap * NT;                      // [NT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ccnt + NT);    // 8-byte aligned: all sizes are multiples of 8
+  // bars: full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2], afull
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * kMaxStages), bar_tempty = smem_u32(bars + 2 * kMaxStages + 2);
+  const uint32_t bar_afull = smem_u32(bars + 2 * kMaxStages + 4);
+  const int n_tiles = (p.m_items + TN - 1) / TN;
+  const int S = p.stages;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 128);
+    }
+    mbar_init(bar_afull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(2 * TN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ producer
+    if (lane == 0) {
+      mbar_expect_tx(bar_afull, kABytes);
+      bulk_g2s(smem_u32(sA), reinterpret_cast<const unsigned char*>(p.a_packed) + (size_t)blockIdx.x * kABytes,
+               kABytes, bar_afull);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % S;
+        if (j >= S) mbar_wait(bar_empty + 8 * s, ((j / S) - 1) & 1);
+        mbar_expect_tx(bar_full + 8 * s, kBBytes);
+        bulk_g2s(smem_u32(sB + (size_t)s * kBBytes),
+                 reinterpret_cast<const unsigned char*>(p.b_packed) + (size_t)j * kBBytes, kBBytes,
+                 bar_full + 8 * s);
+      }
+      // tail: do not exit while a tcgen05.commit may still arrive on an smem barrier
+      for (int j = n_tiles > S ? n_tiles - S : 0; j < n_tiles; ++j)
+        mbar_wait(bar_empty + 8 * (j % S), (j / S) & 1);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      mbar_wait(bar_afull, 0);
+      const uint64_t adesc0 = make_desc(smem_u32(sA), kUM * 16, 128);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % S, a = j & 1;
+        if (j >= 2) mbar_wait(bar_tempty + 8 * a, ((j >> 1) - 1) & 1);
+        mbar_wait(bar_full + 8 * s, (j / S) & 1);
+        tc_fence_after();
+        const uint64_t bdesc0 = make_desc(smem_u32(sB + (size_t)s * kBBytes), TN * 16, 128);
+#pragma unroll
+        for (int kk = 0; kk < kKSteps; ++kk) {
+          // one K=16 step = two 16-byte k-chunks = 2*LBO bytes further along
+          const uint64_t ad = adesc0 + (uint64_t)((kk * 2 * kUM * 16) >> 4);
+          const uint64_t bd = bdesc0 + (uint64_t)((kk * 2 * TN * 16) >> 4);
+          tc_mma_bf16(tmem_base + a * TN, ad, bd, kIdesc, kk > 0 ? 1u : 0u);
+        }
+        tc_commit(bar_empty + 8 * s);   // smem stage reusable once these MMAs retire
+        tc_commit(bar_tfull + 8 * a);   // accumulator stage ready for the epilogue
+      }
+    }
+  } else if (warp >= kFrontWarps) {
+    // ------------------------------------------------ epilogue: thread == user row
+    const int ew = warp - kFrontWarps;
+    const int grp = ew >> 2;
+    const int q = warp & 3;                       // TMEM sub-partition this warp may read
+    const int row = 32 * q + lane;                // row inside the user tile == TMEM lane
+    const int t = grp * 128 + row;                // slot in the candidate arrays
+    const int64_t grow = (int64_t)blockIdx.x * kUM + row;
+    const bool live = grow < p.n_eval;
+    const int32_t* my_pos = p.pos_sorted;
+    int my_npos = 0;
+    if (live) {
+      const int64_t u = p.user_ids[grow];
+      const int64_t b = p.pos_rowptr[u];
+      my_pos = p.pos_sorted + b;
+      my_npos = (int)(p.pos_rowptr[u + 1] - b);
+    }
+    float* mv = cval + t;
+    int* mi = cidx + t;
+    Sel sel;
+    sel.thr = live ? -INFINITY : INFINITY;
+    sel.cnt = 0;
+    sel.sorted = 0;
+    const int trig = p.cap - 12;
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+
+    for (int j = (GROUPS == 2 ? grp : 0); j < n_tiles; j += GROUPS) {
+      const int a = j & 1;
+      mbar_wait(bar_tfull + 8 * a, (j >> 1) & 1);
+      tc_fence_after();
+      const int item_tile0 = j * TN;
+#pragma unroll 1
+      for (int c = 0; c < TN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();
+        tc_ld32(tmem_base + lane_base + (uint32_t)(a * TN + c * 32), r);
+        tc_wait_ld();
+        const int item0 = item_tile0 + c * 32;
+        if (item0 >= p.m_items) break;            // warp-uniform: padded tail of the last tile
+        if (item0 + 32 > p.m_items) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (item0 + i >= p.m_items) r[i] = 0xff800000u;  // -inf
+        }
+        if (p.dense != nullptr && live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (item0 + i < p.m_items) p.dense[grow * p.m_items + item0 + i] = __uint_as_float(r[i]);
+        }
+        if (max32(r) > sel.thr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float v = __uint_as_float(r[i]);
+            if (v > sel.thr)
+              sel = sel_append(sel, v, item0 + i, my_pos, my_npos, p.mask_value, mv, mi, NT, p.cap, p.k);
+          }
+        }
+        if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * a);
+    }
+
+    sel = sel_compact(sel, mv, mi, NT, p.k);
+    ccnt[t] = sel.cnt;
+    if (GROUPS == 2) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+    if (grp == 0 && live) {
+      const int na = sel.cnt;
+      const int nb = GROUPS == 2 ? ccnt[t + 128] : 0;
+      const float* bv = cval + t + 128;
+      const int* bi = cidx + t + 128;
+      int ia = 0, ib = 0;
+      for (int o = 0; o < p.k; ++o) {
+        const bool ha = ia < na, hb = ib < nb;
+        float v = -INFINITY;
+        int id = -1;
+        if (ha || hb) {
+          const float va = ha ? mv[ia * NT] : 0.f, vb = hb ? bv[ib * NT] : 0.f;
+          const int xa = ha ? mi[ia * NT] : 0, xb = hb ? bi[ib * NT] : 0;
+          const bool take_a = ha && (!hb || va > vb || (va == vb && xa < xb));
+          if (take_a) { v = va; id = xa; ++ia; } else { v = vb; id = xb; ++ib; }
+        }
+        p.out_idx[grow * p.k + o] = id;
+        p.out_val[grow * p.k + o] = v;
+      }
+    }
+  }
+
+  // ------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TN));
+  }
+}
+
+constexpr size_t kSmemLimit = 227 * 1024;
+
+template <int D, int TN, int GROUPS>
+static int launch(const Params& p0, cudaStream_t st) {
+  Params p = p0;
+  constexpr int NT = GROUPS * 128;
+  const size_t a_bytes = (size_t)kUM * D * 2, b_bytes = (size_t)TN * D * 2;
+  const size_t cand = (size_t)p.cap * NT * 8 + (size_t)NT * 4;
+  const size_t tail = (2 * 8 + 5) * 8 + 16;
+  if (a_bytes + cand + tail + 2 * b_bytes > kSmemLimit) {
+    set_last_error("k=%d does not fit the tensor-core top-k shared-memory budget", p.k);
+    return LGCN_ERR_UNSUPPORTED;
+  }
+  int stages = (int)((kSmemLimit - a_bytes - cand - tail) / b_bytes);
+  if (stages > 4) stages = 4;
+  p.stages = stages;
+  const size_t smem = a_bytes + (size_t)stages * b_bytes + cand + tail;
+  auto kern = score_topk_tc_kernel<D, TN, GROUPS>;
+  LGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (p.n_eval + kUM - 1) / kUM;
+  kern<<<grid, (kFrontWarps + 4 * GROUPS) * 32, smem, st>>>(p);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
+template <int D, int TN>
+static int run(const float* user_emb, const float* item_emb, const int64_t* user_ids, int n_eval,
+               int m_items, const int64_t* pos_rowptr, const int32_t* pos_sorted, int k,
+               float mask_value, int32_t* out_idx, float* out_val, float* dense, void* workspace,
+               size_t workspace_bytes, cudaStream_t st) {
+  const int64_t n_ut = (n_eval + kUM - 1) / kUM, n_it = ((int64_t)m_items + TN - 1) / TN;
+  const size_t a_total = (size_t)n_ut * kUM * D * 2, b_total = (size_t)n_it * TN * D * 2;
+  if (workspace == nullptr || workspace_bytes < a_total + b_total) {
+    set_last_error("score_topk (bf16) needs a %zu-byte workspace, got %zu", a_total + b_total,
+                   workspace_bytes);
+    return LGCN_ERR_INVALID_ARG;
+  }
+  uint4* a_packed = reinterpret_cast<uint4*>(workspace);
+  uint4* b_packed = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(workspace) + a_total);
+  const int cap_blocks = kSmCount * 8;
+  {
+    const int64_t tot = n_ut * kUM * (D / 8);
+    const int64_t blocks = (tot + 255) / 256;
+    pack_bf16_kernel<<<(unsigned)(blocks < cap_blocks ? blocks : cap_blocks), 256, 0, st>>>(
+        user_emb, user_ids, n_eval, D, kUM, n_ut, a_packed);
+    LGCN_LAUNCH_OK();
+  }
+  {
+    const int64_t tot = n_it * TN * (D / 8);
+    const int64_t blocks = (tot + 255) / 256;
+    pack_bf16_kernel<<<(unsigned)(blocks < cap_blocks ? blocks : cap_blocks), 256, 0, st>>>(
+        item_emb, nullptr, m_items, D, TN, n_it, b_packed);
+    LGCN_LAUNCH_OK();
+  }
+  Params p;
+  p.a_packed = a_packed; p.b_packed = b_packed; p.user_ids = user_ids;
+  p.n_eval = n_eval; p.m_items = m_items; p.pos_rowptr = pos_rowptr; p.pos_sorted = pos_sorted;
+  p.k = k; p.mask_value = mask_value; p.out_idx = out_idx; p.out_val = out_val; p.dense = dense;
+  p.stages = 2;
+  if (k <= 24) {
+    p.cap = 48;
+    return launch<D, TN, 2>(p, st);
+  }
+  int cap = 2 * k;
+  if (cap < 64) cap = 64;
+  if (cap > 128) cap = 128;
+  if (k > cap - 16) {
+    set_last_error("tensor-core top-k supports k <= 112 (got %d); use precision LGCN_F32", k);
+    return LGCN_ERR_UNSUPPORTED;
+  }
+  p.cap = cap;
+  return launch<D, TN, 1>(p, st);
+}
+
+}  // namespace tc
+
+size_t score_topk_tc_workspace(int64_t n_eval, int64_t m_items, int d) {
+  const int tn = d >= 128 ? 128 : 256;
+  const int64_t n_ut = (n_eval + tc::kUM - 1) / tc::kUM, n_it = (m_items + tn - 1) / tn;
+  return (size_t)n_ut * tc::kUM * d * 2 + (size_t)n_it * tn * d * 2;
+}
+
+int score_topk_tc(const float* user_emb, const float* item_emb, const int64_t* user_ids,
+                  int64_t n_eval, int64_t m_items, int d, const int64_t* pos_rowptr,
+                  const int32_t* pos_sorted, int k, float mask_value, int32_t* out_idx,
+                  float* out_val, float* dense, void* workspace, size_t workspace_bytes,
+                  cudaStream_t st) {
+  switch (d) {
+    case 32: return tc::run<32, 256>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes, st);
+    case 64: return tc::run<64, 256>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes, st);
+    case 128: return tc::run<128, 128>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes, st);
+    default:
+      set_last_error("unsupported embedding width d=%d (supported: 32, 64, 128)", d);
+      return LGCN_ERR_UNSUPPORTED;
+  }
 }
 
 }  // namespace lgcn

@@ -140,10 +140,23 @@ def compact_triples(triples: torch.Tensor, valid: torch.Tensor) -> torch.Tensor:
     return out[: int(n_out.item())]
 
 
+_WORKSPACES = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """Grow-only scratch per device (bf16 operand tiles of the tensor-core scorer)."""
+    t = _WORKSPACES.get(dev)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        _WORKSPACES[dev] = t
+    return t
+
+
 def score_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, user_ids: torch.Tensor,
                pos_rowptr: torch.Tensor, pos_sorted: torch.Tensor, k: int,
-               mask_value: float = MASK_VALUE, precision: str = "fp32"):
-    """Fused score + mask + top-k.  Returns (idx int32[U,k], val fp32[U,k])."""
+               mask_value: float = MASK_VALUE, precision: str = "fp32", return_scores: bool = False):
+    """Fused score + mask + top-k.  Returns (idx int32[U,k], val fp32[U,k]) and, with
+    return_scores (tests, small shapes), the dense scores the selection saw."""
     lib = _lib.load()
     U = user_ids.numel()
     m, d = item_emb.shape
@@ -151,11 +164,17 @@ def score_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, user_ids: torch.T
     idx = torch.empty((U, k), dtype=torch.int32, device=dev)
     val = torch.empty((U, k), dtype=torch.float32, device=dev)
     prec = {"fp32": _lib.F32, "bf16": _lib.BF16}[precision]
-    _lib.check(lib.lgcn_score_topk(
-        _chk(user_emb, torch.float32, "user_emb"), _chk(item_emb, torch.float32, "item_emb"),
-        _chk(user_ids, torch.int64, "user_ids"), U, m, d, _chk(pos_rowptr, torch.int64, "pos_rowptr"),
-        _chk(pos_sorted, torch.int32, "pos_sorted"), k, mask_value, prec, idx.data_ptr(), val.data_ptr(),
-        _stream()), "lgcn_score_topk")
+    nbytes = int(lib.lgcn_score_topk_workspace_bytes(U, m, d, prec))
+    ws = _workspace(dev, nbytes) if nbytes else None
+    args = [_chk(user_emb, torch.float32, "user_emb"), _chk(item_emb, torch.float32, "item_emb"),
+            _chk(user_ids, torch.int64, "user_ids"), U, m, d, _chk(pos_rowptr, torch.int64, "pos_rowptr"),
+            _chk(pos_sorted, torch.int32, "pos_sorted"), k, mask_value, prec, idx.data_ptr(), val.data_ptr(),
+            ws.data_ptr() if ws is not None else 0, nbytes]
+    if return_scores:
+        dense = torch.empty((U, m), dtype=torch.float32, device=dev)
+        _lib.check(lib.lgcn_score_topk_debug(*args, dense.data_ptr(), _stream()), "lgcn_score_topk_debug")
+        return idx, val, dense
+    _lib.check(lib.lgcn_score_topk(*args, _stream()), "lgcn_score_topk")
     return idx, val
 
 

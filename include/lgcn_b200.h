@@ -178,11 +178,25 @@ int lgcn_compact_triples(const int64_t* triples, const uint8_t* valid, int64_t c
  *   user_ids: int64[n_eval] rows of user_emb to score
  *   precision: LGCN_F32 exact fp32 FMA scores | LGCN_BF16 tcgen05 tensor cores
  * out_idx int32[n_eval,k] (sorted by score desc, id asc), out_val fp32[n_eval,k].
+ * workspace: lgcn_score_topk_workspace_bytes() bytes of device scratch (may be NULL for F32).
  * ------------------------------------------------------------------------ */
 int lgcn_score_topk(const float* user_emb, const float* item_emb, const int64_t* user_ids,
                     int64_t n_eval, int64_t m_items, int d, const int64_t* pos_rowptr,
                     const int32_t* pos_sorted, int k, float mask_value, int precision,
-                    int32_t* out_idx, float* out_val, lgcn_stream_t stream);
+                    int32_t* out_idx, float* out_val, void* workspace, int64_t workspace_bytes,
+                    lgcn_stream_t stream);
+
+/* Bytes of device scratch lgcn_score_topk needs (bf16 operand tiles of the tensor-core
+ * path; 0 for LGCN_F32). */
+int64_t lgcn_score_topk_workspace_bytes(int64_t n_eval, int64_t m_items, int d, int precision);
+
+/* Test aid: same as lgcn_score_topk, and also dumps the scores the selection saw
+ * (the TMEM accumulators for LGCN_BF16) to dense_scores[n_eval, m_items]. */
+int lgcn_score_topk_debug(const float* user_emb, const float* item_emb, const int64_t* user_ids,
+                          int64_t n_eval, int64_t m_items, int d, const int64_t* pos_rowptr,
+                          const int32_t* pos_sorted, int k, float mask_value, int precision,
+                          int32_t* out_idx, float* out_val, void* workspace,
+                          int64_t workspace_bytes, float* dense_scores, lgcn_stream_t stream);
 
 /* Debug/test aid: the dense fp32 score block the F32 top-k path selects from
  * (same FMA order), scores[n_eval, m_items].  Small shapes only. */
