@@ -22,8 +22,10 @@
 //                  survivors are checked against the user's train positives
 //                  (binary search) and appended to a per-row shared-memory
 //                  buffer that is compacted warp-synchronously to the sorted
-//                  top-k.  Two epilogue groups take alternate accumulator stages
-//                  and are merged at the end (k <= 24); one group for larger k.
+//                  top-k.  Train positives are masked by walking the user's sorted
+//                  list in step with the sweep.  Two epilogue groups split the columns
+//                  of every tile and are merged at the end (k <= 24); one group for
+//                  larger k.  The other accumulator stage is being filled meanwhile.
 // Ties: items arrive in ascending id inside a thread, filters are strict, the
 // final merge orders by (score desc, id asc) => lowest id wins, as in the fp32 path.
 #include "common.cuh"
@@ -50,21 +52,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  // the last operand is a suspend-time hint: a waiting thread sleeps in hardware instead of
+  // burning issue slots the epilogue warps of the same SM sub-partition need
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps after ~2 s instead of hanging the GPU.
+// Bounded wait: a protocol bug traps after a few seconds instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if ((++spins & 0xfffu) == 0 && clock64() - t0 > 8000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -146,15 +151,6 @@ struct Sel {
   int sorted;  // entries [0, sorted) are ordered by (value desc, id asc)
 };
 
-__device__ __forceinline__ bool pos_contains(const int32_t* __restrict__ a, int n, int32_t x) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid;
-  }
-  return lo < n && __ldg(a + lo) == x;
-}
-
 // Fold the unsorted tail [sorted, cnt) into the sorted top-k prefix.  New entries carry
 // larger ids than everything already held, so on equal value they go AFTER (strict <).
 __device__ __noinline__ Sel sel_compact(Sel s, float* cval, int* cidx, int NT, int k) {
@@ -181,29 +177,53 @@ __device__ __noinline__ Sel sel_compact(Sel s, float* cval, int* cidx, int NT, i
   return s;
 }
 
-__device__ __noinline__ Sel sel_append(Sel s, float raw, int item, const int32_t* pos, int npos,
-                                       float mask_value, float* cval, int* cidx, int NT, int cap, int k) {
-  const float v = pos_contains(pos, npos, item) ? mask_value : raw;  // trainer.py:137
-  if (!(v > s.thr)) return s;
-  if (s.cnt == cap) {  // rare (only while the threshold is still -inf): keep the buffer bounded
-    s = sel_compact(s, cval, cidx, NT, k);
-    if (!(v > s.thr)) return s;
+// Per-thread walk of the user's sorted train positives.  Candidates reach sel_append in
+// ascending item id, so membership is a pointer advance, not a search.
+struct PosWalk {
+  const int32_t* pos;
+  int n, pp, next;
+};
+
+struct SelWalk {
+  Sel s;
+  int pp, next;
+};
+
+// Out of line on purpose: the call sites sit in the hot loop and must stay small
+// (the unrolled epilogue is instruction-cache bound otherwise).
+__device__ __noinline__ SelWalk sel_append(Sel s, int pp, int next, const int32_t* pos, int npos, float raw,
+                                           int item, int m_items, float mask_value, float* cval, int* cidx,
+                                           int NT, int cap, int k) {
+  SelWalk out;
+  while (next < item) {
+    ++pp;
+    next = pp < npos ? __ldg(pos + pp) : 0x7fffffff;
   }
-  cval[s.cnt * NT] = v;
-  cidx[s.cnt * NT] = item;
-  ++s.cnt;
-  return s;
+  out.pp = pp;
+  out.next = next;
+  const float v = next == item ? mask_value : raw;  // trainer.py:137  rating[...] = -(1<<10)
+  if (item < m_items && v > s.thr) {                // item >= m_items: zero padding of the last tile
+    if (s.cnt == cap) s = sel_compact(s, cval, cidx, NT, k);  // rare: threshold still -inf
+    if (v > s.thr) {
+      cval[s.cnt * NT] = v;
+      cidx[s.cnt * NT] = item;
+      ++s.cnt;
+    }
+  }
+  out.s = s;
+  return out;
 }
 
-__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
+// max over 8-element blocks (m4[b] covers r[8b .. 8b+7]) and over the whole chunk
+__device__ __forceinline__ float max32(const uint32_t (&r)[32], float (&m4)[4]) {
   float m[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) m[i] = fmaxf(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
 #pragma unroll
   for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[2 * i], m[2 * i + 1]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) m[i] = fmaxf(m[2 * i], m[2 * i + 1]);
-  return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+  for (int i = 0; i < 4; ++i) m4[i] = fmaxf(m[2 * i], m[2 * i + 1]);
+  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
 }
 
 struct Params {
@@ -220,7 +240,7 @@ struct Params {
   float* dense;            // optional [n_eval, m_items] dump of the accumulators (tests)
 };
 
-template <int D, int TN, int GROUPS>
+template <int D, int TN, int GROUPS, bool DUMP>
 __global__ void __launch_bounds__((kFrontWarps + 4 * GROUPS) * 32, 1)
 score_topk_tc_kernel(const Params p) {
   constexpr int NT = GROUPS * 128;              // epilogue threads
@@ -254,7 +274,7 @@ score_topk_tc_kernel(const Params p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 128);
+      mbar_init(bar_tempty + 8 * a, 128 * GROUPS);
     }
     mbar_init(bar_afull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -334,36 +354,50 @@ score_topk_tc_kernel(const Params p) {
     sel.sorted = 0;
     const int trig = p.cap - 12;
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+    // walk of the user's sorted train positives, in step with the item sweep
+    int pp = 0;
+    int next_pos = my_npos > 0 ? __ldg(my_pos) : 0x7fffffff;
+    // both epilogue groups work on every tile; group g owns the chunks [g*CPG, (g+1)*CPG)
+    constexpr int CPG = TN / 32 / GROUPS;
+    const int c0 = grp * CPG;
 
-    for (int j = (GROUPS == 2 ? grp : 0); j < n_tiles; j += GROUPS) {
+    for (int j = 0; j < n_tiles; ++j) {
       const int a = j & 1;
       mbar_wait(bar_tfull + 8 * a, (j >> 1) & 1);
       tc_fence_after();
-      const int item_tile0 = j * TN;
+      const int item_tile0 = j * TN + c0 * 32;
+      const uint32_t tbase = tmem_base + lane_base + (uint32_t)(a * TN + c0 * 32);
 #pragma unroll 1
-      for (int c = 0; c < TN / 32; ++c) {
+      for (int cc = 0; cc < CPG; ++cc) {
         uint32_t r[32];
         __syncwarp();
-        tc_ld32(tmem_base + lane_base + (uint32_t)(a * TN + c * 32), r);
+        tc_ld32(tbase + (uint32_t)(cc * 32), r);
         tc_wait_ld();
-        const int item0 = item_tile0 + c * 32;
-        if (item0 >= p.m_items) break;            // warp-uniform: padded tail of the last tile
-        if (item0 + 32 > p.m_items) {
+        const int item0 = item_tile0 + cc * 32;
+        if (DUMP) {
+          if (live) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (item0 + i >= p.m_items) r[i] = 0xff800000u;  // -inf
+            for (int i = 0; i < 32; ++i)
+              if (item0 + i < p.m_items) p.dense[grow * p.m_items + item0 + i] = __uint_as_float(r[i]);
+          }
         }
-        if (p.dense != nullptr && live) {
+        float m4[4];
+        if (max32(r, m4) > sel.thr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (item0 + i < p.m_items) p.dense[grow * p.m_items + item0 + i] = __uint_as_float(r[i]);
-        }
-        if (max32(r) > sel.thr) {
+          for (int b = 0; b < 4; ++b) {
+            if (m4[b] > sel.thr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = __uint_as_float(r[i]);
-            if (v > sel.thr)
-              sel = sel_append(sel, v, item0 + i, my_pos, my_npos, p.mask_value, mv, mi, NT, p.cap, p.k);
+              for (int i = 8 * b; i < 8 * b + 8; ++i) {
+                const float v = __uint_as_float(r[i]);
+                if (v > sel.thr) {
+                  const SelWalk w = sel_append(sel, pp, next_pos, my_pos, my_npos, v, item0 + i, p.m_items,
+                                               p.mask_value, mv, mi, NT, p.cap, p.k);
+                  sel = w.s;
+                  pp = w.pp;
+                  next_pos = w.next;
+                }
+              }
+            }
           }
         }
         if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
@@ -423,10 +457,17 @@ static int launch(const Params& p0, cudaStream_t st) {
   if (stages > 4) stages = 4;
   p.stages = stages;
   const size_t smem = a_bytes + (size_t)stages * b_bytes + cand + tail;
-  auto kern = score_topk_tc_kernel<D, TN, GROUPS>;
-  LGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (p.n_eval + kUM - 1) / kUM;
-  kern<<<grid, (kFrontWarps + 4 * GROUPS) * 32, smem, st>>>(p);
+  const int threads = (kFrontWarps + 4 * GROUPS) * 32;
+  if (p.dense != nullptr) {
+    auto kern = score_topk_tc_kernel<D, TN, GROUPS, true>;
+    LGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(p);
+  } else {
+    auto kern = score_topk_tc_kernel<D, TN, GROUPS, false>;
+    LGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(p);
+  }
   LGCN_LAUNCH_OK();
   return 0;
 }
