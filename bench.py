@@ -258,10 +258,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
         def eval_pass(precision):
             sums = torch.zeros((4, 2), dtype=torch.float64, device=dev)
-            for s0 in range(0, len(ev_users), 10000):          # test_u_batch_size (parse.py:24)
-                bu = ev_users[s0:s0 + 10000]
-                idx, _ = model.getUsersTopK(bu, 20, precision=precision)
-                lmetric.batch_metric_sums(idx, bu, rp, srt, (10, 20), sums)
+            idx, _ = model.getUsersTopK(ev_users, 20, precision=precision)   # one launch: nothing is materialised
+            lmetric.batch_metric_sums(idx, ev_users, rp, srt, (10, 20), sums)
             return sums
 
         def timed(fn, reps):

@@ -28,6 +28,8 @@
 //                  larger k.  The other accumulator stage is being filled meanwhile.
 // Ties: items arrive in ascending id inside a thread, filters are strict, the
 // final merge orders by (score desc, id asc) => lowest id wins, as in the fp32 path.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lgcn {
@@ -238,6 +240,7 @@ struct Params {
   int32_t* out_idx;
   float* out_val;
   float* dense;            // optional [n_eval, m_items] dump of the accumulators (tests)
+  int debug_mode;          // 0 = normal; 1 = epilogue skips the TMEM reads (pipeline experiments)
 };
 
 template <int D, int TN, int GROUPS, bool DUMP>
@@ -368,7 +371,7 @@ score_topk_tc_kernel(const Params p) {
       const int item_tile0 = j * TN + c0 * 32;
       const uint32_t tbase = tmem_base + lane_base + (uint32_t)(a * TN + c0 * 32);
 #pragma unroll 1
-      for (int cc = 0; cc < CPG; ++cc) {
+      for (int cc = 0; cc < (p.debug_mode == 1 ? 0 : CPG); ++cc) {
         uint32_t r[32];
         __syncwarp();
         tc_ld32(tbase + (uint32_t)(cc * 32), r);
@@ -506,6 +509,10 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
   p.n_eval = n_eval; p.m_items = m_items; p.pos_rowptr = pos_rowptr; p.pos_sorted = pos_sorted;
   p.k = k; p.mask_value = mask_value; p.out_idx = out_idx; p.out_val = out_val; p.dense = dense;
   p.stages = 2;
+  {
+    const char* dbg = getenv("LGCN_TC_DEBUG");
+    p.debug_mode = dbg ? atoi(dbg) : 0;
+  }
   if (k <= 24) {
     p.cap = 48;
     return launch<D, TN, 2>(p, st);

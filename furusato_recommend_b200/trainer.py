@@ -54,15 +54,22 @@ class Trainer:
     def _eval_users(self) -> torch.Tensor:
         return torch.from_numpy(self.dataset.test_users()).to(self.device)  # list(testDict.keys()), :118
 
+    def _eval_batch(self) -> int:
+        """The reference batches users (test_u_batch_size=10000, parse.py:24) only because it
+        materialises a [U_b, m] score matrix; the fused kernel does not, so small batches would
+        just leave SMs idle (128 users per CTA).  Results do not depend on the batch size."""
+        return max(int(self.config.get("test_u_batch_size", 10000)), 1 << 17)
+
     @torch.no_grad()
     def get_topk_list(self, k: int = 50) -> List[torch.Tensor]:
         """trainer.py:83-113: per user batch, int64 [U_b, k] on the host."""
         self.model.eval()
         users = self._eval_users()
         out = []
-        for bu in minibatch(users, batch_size=int(self.config["test_u_batch_size"])):
-            idx, _ = self.model.getUsersTopK(bu, k)
-            out.append(idx.to(torch.int64).cpu())
+        idx_all = torch.cat([self.model.getUsersTopK(bu, k)[0] for bu in minibatch(users, batch_size=self._eval_batch())])
+        # same list-of-batches shape as the reference (one int64 [U_b, k] tensor per test_u_batch_size users)
+        for s0 in range(0, len(users), int(self.config["test_u_batch_size"])):
+            out.append(idx_all[s0:s0 + int(self.config["test_u_batch_size"])].to(torch.int64).cpu())
         return out
 
     @torch.no_grad()
@@ -73,7 +80,7 @@ class Trainer:
         test_rowptr, test_sorted = self.dataset.test_csr()
         kmax = max(self.topks)
         sums = torch.zeros((4, len(self.topks)), dtype=torch.float64, device=self.device)
-        for bu in minibatch(users, batch_size=int(self.config["test_u_batch_size"])):
+        for bu in minibatch(users, batch_size=self._eval_batch()):
             idx, _ = self.model.getUsersTopK(bu, kmax)
             metric.batch_metric_sums(idx, bu, test_rowptr, test_sorted, self.topks, sums)
         res = metric.finalize(sums, len(users))
