@@ -172,15 +172,28 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
-    # weak scaling: every rank trains its own cfg-2-sized graph shard (seed differs per rank)
-    n, m, tu, ti, su, si = bipartite(CFG2["n_users"], CFG2["m_items"], CFG2["n_interactions"], seed=CFG2["seed"] + rank)
+    # weak scaling: the graph grows with the number of GPUs (world x cfg-2), rows are
+    # partitioned over the ranks (nnz-balanced) and every layer all-gathers over NVLink
+    n, m, tu, ti, su, si = bipartite(CFG2["n_users"] * world, CFG2["m_items"] * world,
+                                     CFG2["n_interactions"] * world, seed=CFG2["seed"])
     cfg = dict(recdim=CFG2["d"], layer=CFG2["layers"], lr=CFG2["lr"], decay=CFG2["decay"],
                bpr_batch_size=CFG2["batch"], device=dev, test_u_batch_size=10000, storage_dtype=args.storage)
     ds = BasicDataset(n, m, tu.numpy(), ti.numpy(), su.numpy(), si.numpy(), config=cfg, device=dev)
     torch.manual_seed(2020 + rank)
-    model = LightGCN(cfg, ds)
-    model.train()
-    N, nnz, K, d, B = n + m, model.graph.nnz, CFG2["layers"], CFG2["d"], CFG2["batch"]
+    K, d, B = CFG2["layers"], CFG2["d"], CFG2["batch"]
+    if world == 1:
+        model = LightGCN(cfg, ds)
+        model.train()
+        nnz = model.graph.nnz
+        fused = model._fused_step
+        launches_per_step = 2 * K + 2
+    else:
+        from furusato_recommend_b200.parallel import DistLightGCN
+        model = DistLightGCN(cfg, ds, rank, world)
+        nnz = ds.csr_graph().nnz
+        fused = model.fused_step
+        launches_per_step = 2 * K + 2
+    N = n + m
 
     S = UniformSample(ds, seed=CFG2["seed"], epoch=0)
     n_batches = len(S) // B
@@ -189,7 +202,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     def step(i):
         b = (i % n_batches) * B
-        model._fused_step(users[b:b + B], pos[b:b + B], neg[b:b + B])
+        fused(users[b:b + B], pos[b:b + B], neg[b:b + B])
 
     def barrier():
         if world > 1:
@@ -231,15 +244,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- e2e: public API with pinned host triples, H2D + loss D2H inside the timed region ----
     S_host = S.cpu()
     hu, hp, hn = (S_host[:, j].contiguous().pin_memory() for j in range(3))
+
+    def e2e_step(b):
+        if world == 1:
+            return model.stageOne(hu[b:b + B], hp[b:b + B], hn[b:b + B]).item()
+        du, dp, dn = (t[b:b + B].to(dev, non_blocking=True) for t in (hu, hp, hn))
+        return model.fused_step(du, dp, dn).item()
+
     for i in range(3):
-        model.stageOne(hu[:B], hp[:B], hn[:B]).item()
+        e2e_step(0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        b = (i % n_batches) * B
-        loss = model.stageOne(hu[b:b + B], hp[b:b + B], hn[b:b + B])
-        loss.item()
+        e2e_step((i % n_batches) * B)
     e1.record()
     barrier()
     t_e2e = e0.elapsed_time(e1) / 1e3
@@ -247,7 +265,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- eval half of the metric: full-rank top-20 users/s ----
     eval_info = None
-    if not args.no_eval:
+    if not args.no_eval and world == 1:
         model.eval()
         tr = Trainer(cfg, ds, model)
         ev_users = tr._eval_users()
@@ -315,16 +333,28 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         t = torch.tensor([t_dev, t_e2e, spmm_avg_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e, spmm_avg_s = (float(x) for x in t)
-        tot = torch.tensor([float(nnz)], device=dev, dtype=torch.float64)
-        dist.all_reduce(tot)
-        nnz_total = float(tot)
-    else:
-        nnz_total = float(nnz)
+    nnz_total = float(nnz)  # the partitioned graph is ONE graph: every rank reports its global nnz
+    dist_eval = None
+    if world > 1 and not args.no_eval:
+        ev_users = torch.from_numpy(ds.test_users()).to(dev)
+        model.computer_local()
+        model.topk_user_shard(ev_users, 20)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        mine, idx, _ = model.topk_user_shard(ev_users, 20)
+        q1.record()
+        barrier()
+        te = torch.tensor([q0.elapsed_time(q1) / 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist_eval = {"metric": "full-rank top-20 eval users/sec, user-sharded (incl. all-gather of light_out)",
+                     "value": len(ev_users) / float(te), "unit": "users/s", "users": int(len(ev_users)), "items": m,
+                     "precision": "bf16 tcgen05 (fp32 accumulate)"}
 
     if rank == 0:
         hbm_peak, _, which = measured_peaks()
         s_bytes = 2 if args.storage == "bf16" else 4
-        layer_bytes = spmm_layer_bytes(nnz, N, d, s_bytes)
+        layer_bytes = spmm_layer_bytes(nnz // world, N // world, d, s_bytes)  # per rank, per launch
         achieved = layer_bytes / spmm_avg_s / 1e9
         traffic = None
         tp = REPO / "profiles" / "spmm_traffic.json"
@@ -336,13 +366,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.storage == "fp32" else "bf16-storage/f32-acc",
             "data": "synthetic",
-            "config": {"workload": f"cfg-2: LightGCN {K}-layer d={d} BPR B={B} on a synthetic five-core bipartite graph "
-                                   f"{n} users x {m} items, nnz(A_hat)={nnz} per GPU",
+            "config": {"workload": f"cfg-2{' x%d' % world if world > 1 else ''}: LightGCN {K}-layer d={d} BPR B={B} on a synthetic "
+                                   f"five-core bipartite graph {n} users x {m} items, nnz(A_hat)={nnz}",
                        "l2": "256 MiB buffer written between timed steps (L2 flush, untimed)",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent cfg-2 graph shards (no collective)"},
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"{world} GPUs: rows partitioned by nnz, per-layer NCCL all-gather (2K per step) + one 3B-row all-reduce"},
             "e2e": {"value": nnz_total * K / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 3 * B * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps * 1e3},
-            "gpu_launches": (2 * K + 2) * args.steps,
+            "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "spmm_layer_kernel", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which,
                          "bytes_per_launch": layer_bytes, "avg_launch_us": spmm_avg_s * 1e6,
@@ -352,6 +383,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         }
         if eval_info:
             out["eval"] = eval_info
+        if dist_eval:
+            out["eval"] = dist_eval
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             t_cpu = cpu_train_steps((n, m, tu.numpy(), ti.numpy()), 5, 2, threads)

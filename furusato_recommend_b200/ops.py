@@ -51,9 +51,10 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
                     betas=(0.9, 0.999), eps: float = 1e-8, zero_base: bool = False) -> None:
     """lgcn_propagate_layer: one normalised-adjacency SpMM + fused row epilogue."""
     lib = _lib.load()
-    N, d = src.shape
-    if N != g.n_nodes:
-        raise ValueError(f"src has {N} rows, graph has {g.n_nodes} nodes")
+    n_src, d = src.shape
+    N = g.n_nodes  # rows of this (possibly rank-local) graph; src may hold more rows (all-gathered)
+    if n_src < N:
+        raise ValueError(f"src has {n_src} rows, graph has {N} nodes")
     a = _lib.LayerArgs()
     a.d, a.src_dtype, a.scale_src = d, _dt(src), int(scale_src)
     a.dst_dtype = _dt(dst) if dst is not None else _dt(src)

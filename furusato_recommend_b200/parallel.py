@@ -1,0 +1,252 @@
+"""Row-partitioned LightGCN over the GPUs of one box.
+
+The reference's own "multi-GPU" mode (ddp_lgcn.py:625-746) is replicas that never
+synchronise gradients (it trains through `ddp_model.module.OneEpoch`, so DDP's
+reducer never runs).  The partition used here is the reference's *single-device*
+memory trick promoted to ranks: `_split_A_hat` (dataloader.py:195-205) cuts A_hat
+into contiguous row folds; rank r owns fold r (balanced by nnz, not rows), the
+matching rows of E, Adam state and every X_k.
+
+One exchange per layer: all-gather of the pre-scaled activations dinv (.) X_k
+(forward) or dinv (.) H_j (backward; A_hat is symmetric so no transpose / reduce-
+scatter is needed), then the local SpMM with the usual fused epilogue.  Blocks are
+padded to a common row count R so the collective is a plain all-gather: padded id
+= rank * R + local row, CSR columns are remapped once at partition time.
+
+The BPR step needs <= 3B rows from arbitrary owners: every rank sees the same B
+triples, owners contribute their rows to a [3B, d] buffer (one small all-reduce),
+every rank runs the fused BPR kernel on that compact table and adds the gradient
+rows it owns into its G shard.  The loss is identical on all ranks by construction.
+
+`RowPartition` and `DistPropagator` are plain index / orchestration logic: they are
+unit-tested on CPU with the gloo backend (tests/test_distributed_cpu.py) with the
+local SpMM injected; on GPUs the local op is lgcn_propagate_layer and the
+collectives run over NCCL / NVLink.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class RowPartition:
+    """Contiguous, nnz-balanced row blocks padded to a common size R."""
+
+    def __init__(self, rowptr: torch.Tensor, world: int):
+        N = rowptr.numel() - 1
+        nnz = int(rowptr[-1])
+        targets = (torch.arange(1, world, device=rowptr.device, dtype=torch.float64) * (nnz / world)).to(rowptr.dtype)
+        cuts = torch.searchsorted(rowptr, targets, right=False).clamp_(0, N)
+        starts = torch.cat([torch.zeros(1, dtype=cuts.dtype, device=cuts.device), cuts,
+                            torch.full((1,), N, dtype=cuts.dtype, device=cuts.device)])
+        starts = torch.cummax(starts, 0)[0]
+        self.world, self.n_nodes = world, N
+        self.starts = starts                       # [world + 1] first global row of each block
+        self.R = int((starts[1:] - starts[:-1]).max()) if N else 0
+        self.R = max(self.R, 1)
+
+    def owner(self, ids: torch.Tensor) -> torch.Tensor:
+        return torch.searchsorted(self.starts[1:].contiguous(), ids, right=True).clamp_(max=self.world - 1)
+
+    def to_padded(self, ids: torch.Tensor) -> torch.Tensor:
+        r = self.owner(ids)
+        return r * self.R + (ids - self.starts[r])
+
+    def block(self, rank: int):
+        return int(self.starts[rank]), int(self.starts[rank + 1])
+
+    def local_csr(self, rank: int, rowptr: torch.Tensor, col: torch.Tensor, dinv: torch.Tensor):
+        """(rowptr_local int64[R+1], col_padded int32[nnz_local], dinv_local fp32[R])."""
+        lo, hi = self.block(rank)
+        e0, e1 = int(rowptr[lo]), int(rowptr[hi])
+        rp = torch.full((self.R + 1,), e1 - e0, dtype=torch.int64, device=rowptr.device)
+        rp[: hi - lo + 1] = rowptr[lo:hi + 1] - e0
+        colp = self.to_padded(col[e0:e1].to(torch.int64)).to(torch.int32)
+        dl = torch.zeros(self.R, dtype=dinv.dtype, device=dinv.device)
+        dl[: hi - lo] = dinv[lo:hi]
+        return rp.contiguous(), colp.contiguous(), dl.contiguous()
+
+    def shard(self, rank: int, full: torch.Tensor) -> torch.Tensor:
+        """Rows of a global [N, ...] tensor owned by `rank`, zero-padded to R rows."""
+        lo, hi = self.block(rank)
+        out = torch.zeros((self.R,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
+        out[: hi - lo] = full[lo:hi]
+        return out
+
+    def unshard(self, gathered: torch.Tensor) -> torch.Tensor:
+        """[world*R, ...] padded layout -> global [N, ...]."""
+        parts = []
+        for r in range(self.world):
+            lo, hi = self.block(r)
+            parts.append(gathered[r * self.R: r * self.R + (hi - lo)])
+        return torch.cat(parts)
+
+
+# local_spmm(src_full [W*R, d], *, dst, base, acc_in, acc_out, acc_scale, last_kwargs) -> None
+LocalSpmm = Callable[..., None]
+
+
+class DistPropagator:
+    """K-layer propagation / Horner backward over a RowPartition.
+
+    `local_spmm(src_full, dst=..., base=..., acc_in=..., acc_out=..., acc_scale=..., **kw)` must
+    implement lgcn_propagate_layer's contract with scale_src=0 on the rank's local CSR."""
+
+    def __init__(self, part: RowPartition, rank: int, dinv_local: torch.Tensor, n_layers: int,
+                 local_spmm: LocalSpmm, group=None, storage_dtype: torch.dtype = torch.float32):
+        self.part, self.rank, self.K = part, rank, n_layers
+        self.dinv = dinv_local
+        self.spmm = local_spmm
+        self.group = group
+        self.storage_dtype = storage_dtype
+        self._full: Optional[torch.Tensor] = None
+        self._z = [None, None]
+
+    def _buffers(self, d: int, device):
+        R, W = self.part.R, self.part.world
+        if self._full is None or self._full.shape != (W * R, d):
+            self._full = torch.empty((W * R, d), dtype=self.storage_dtype, device=device)
+            self._z = [torch.empty((R, d), dtype=self.storage_dtype, device=device) for _ in range(2)]
+        return self._full, self._z
+
+    def _gather(self, z_local: torch.Tensor) -> torch.Tensor:
+        full, _ = self._buffers(z_local.shape[1], z_local.device)
+        if self.part.world == 1:
+            full.copy_(z_local)
+        else:
+            dist.all_gather_into_tensor(full, z_local.contiguous(), group=self.group)
+        return full
+
+    def forward(self, emb_local: torch.Tensor, acc: torch.Tensor, out: torch.Tensor) -> None:
+        """out = (X0 + ... + XK)/(K+1) for the local rows."""
+        K = self.K
+        _, z = self._buffers(emb_local.shape[1], emb_local.device)
+        z0 = (self.dinv[:, None] * emb_local).to(self.storage_dtype)
+        src = z0
+        for k in range(K):
+            last = k == K - 1
+            full = self._gather(src)
+            self.spmm(full, dst=None if last else z[k & 1], base=None,
+                      acc_in=emb_local if k == 0 else acc, acc_out=out if last else acc,
+                      acc_scale=1.0 / (K + 1) if last else 1.0)
+            src = z[k & 1]
+
+    def backward(self, G_local: torch.Tensor, **last_kwargs) -> None:
+        """H0 = G, H_{j+1} = G + A_hat H_j; the last layer's epilogue consumes H_K
+        (grad_mode 1 or 2 keyword arguments are passed through to the local op)."""
+        K = self.K
+        _, z = self._buffers(G_local.shape[1], G_local.device)
+        src = (self.dinv[:, None] * G_local).to(self.storage_dtype)
+        for j in range(K):
+            last = j == K - 1
+            full = self._gather(src)
+            kw = last_kwargs if last else {}
+            self.spmm(full, dst=None if last else z[j & 1], base=G_local, acc_in=None, acc_out=None,
+                      acc_scale=1.0, **kw)
+            src = z[j & 1]
+
+
+def exchange_rows(part: RowPartition, rank: int, local: torch.Tensor, padded_ids: torch.Tensor, group=None):
+    """rows[i] = TABLE[padded_ids[i]] where TABLE is row-partitioned: owners fill, one all-reduce."""
+    buf = torch.zeros((padded_ids.numel(), local.shape[1]), dtype=local.dtype, device=local.device)
+    mine = (padded_ids // part.R) == rank
+    buf[mine] = local[(padded_ids[mine] % part.R)]
+    if part.world > 1:
+        dist.all_reduce(buf, group=group)
+    return buf, mine
+
+
+class DistLightGCN:
+    """Row-partitioned LightGCN training step + user-sharded evaluation on CUDA ranks."""
+
+    def __init__(self, config: dict, dataset, rank: int, world: int, group=None, seed: int = 2020):
+        from . import ops
+        from .graph import CsrGraph, decompose_rows
+        self.ops = ops
+        self.config, self.dataset, self.rank, self.world, self.group = config, dataset, rank, world, group
+        self.n, self.m = dataset.n_users, dataset.m_items
+        self.d = int(config["recdim"])
+        self.K = int(config["layer"])
+        self.device = torch.device(config["device"])
+        g = dataset.csr_graph()
+        self.part = RowPartition(g.rowptr, world)
+        rp, colp, dl = self.part.local_csr(rank, g.rowptr, g.col, g.dinv)
+        self.local_graph = CsrGraph(self.part.R, 0, rp, colp, dl, **decompose_rows(rp))
+        self.local_nnz = int(colp.numel())
+        R, d, dev = self.part.R, self.d, self.device
+        gen = torch.Generator(device=dev).manual_seed(seed + rank)
+        self.emb = torch.randn((R, d), generator=gen, device=dev) * 0.1      # model/lgcn.py:75, local rows
+        lo, hi = self.part.block(rank)
+        self.emb[hi - lo:] = 0
+        self.m1, self.v1 = torch.zeros_like(self.emb), torch.zeros_like(self.emb)
+        self.acc, self.out = torch.empty_like(self.emb), torch.empty_like(self.emb)
+        self.G = torch.zeros_like(self.emb)
+        self.cnt = torch.zeros(R, dtype=torch.int32, device=dev)
+        self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.hp = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.work_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        storage = torch.bfloat16 if config.get("storage_dtype") == "bf16" else torch.float32
+        self.prop = DistPropagator(self.part, rank, dl, self.K, self._local_spmm, group, storage)
+        self.collectives_per_step = 2 * self.K + 2
+
+    def load_global_embedding(self, E: torch.Tensor) -> None:
+        """Take this rank's rows of a global [N, d] table (checkpoint key all_embedding.weight)."""
+        self.emb.copy_(self.part.shard(self.rank, E.to(self.device)))
+
+    def gather_embedding(self) -> torch.Tensor:
+        full = torch.empty((self.world * self.part.R, self.d), dtype=torch.float32, device=self.device)
+        if self.world == 1:
+            full.copy_(self.emb)
+        else:
+            dist.all_gather_into_tensor(full, self.emb, group=self.group)
+        return self.part.unshard(full)
+
+    def _local_spmm(self, src_full, **kw):
+        self.ops.propagate_layer(self.local_graph, src_full, scale_src=False, **kw)
+
+    def computer_local(self) -> torch.Tensor:
+        self.prop.forward(self.emb, self.acc, self.out)
+        return self.out
+
+    def fused_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+        """One training step on the same B triples on every rank (global ids)."""
+        ops, part, B = self.ops, self.part, users.numel()
+        self.prop.forward(self.emb, self.acc, self.out)
+        ids = part.to_padded(torch.cat([users, pos + self.n, neg + self.n]))
+        out_c, mine = exchange_rows(part, self.rank, self.out, ids, self.group)
+        emb_c, _ = exchange_rows(part, self.rank, self.emb, ids, self.group)
+        ar = torch.arange(B, device=self.device, dtype=torch.int64)
+        G_c = torch.zeros_like(out_c)
+        cnt_c = torch.zeros(3 * B, dtype=torch.int32, device=self.device)
+        work = torch.empty(2 * B, dtype=torch.float32, device=self.device)
+        decay = float(self.config["decay"])
+        ops.bpr_fwd_bwd(out_c, emb_c, ar, ar, ar + B, B, decay, G_c, cnt_c, self.loss_out, work, self.work_counter)
+        loc = ids[mine] % part.R
+        self.G.index_add_(0, loc, G_c[mine])
+        self.cnt.index_add_(0, loc, cnt_c[mine])
+        ops.adam_tick(self.step_t, self.hp, float(self.config["lr"]))
+        self.prop.backward(self.G, grad_mode=2, inv_layers=1.0 / (self.K + 1), reg_coef=decay / B, cnt=self.cnt,
+                           emb=self.emb, adam_m=self.m1, adam_v=self.v1, adam_hp=self.hp, zero_base=False)
+        self.G.zero_()
+        return self.loss_out[2]
+
+    def gather_out(self) -> torch.Tensor:
+        """Global light_out [N, d] on every rank (eval: the item table is replicated)."""
+        full = torch.empty((self.world * self.part.R, self.d), dtype=torch.float32, device=self.device)
+        if self.world == 1:
+            full.copy_(self.out)
+        else:
+            dist.all_gather_into_tensor(full, self.out, group=self.group)
+        return self.part.unshard(full)
+
+    def topk_user_shard(self, users: torch.Tensor, k: int, precision: str = "bf16"):
+        """Evaluation sharded by user: this rank scores users[rank::world] against all items."""
+        full = self.gather_out()
+        mine = users[self.rank::self.world].contiguous()
+        rowptr, _, srt = self.dataset.pos_csr()
+        idx, val = self.ops.score_topk(full[: self.n].contiguous(), full[self.n:].contiguous(), mine, rowptr, srt, k,
+                                       precision=precision)
+        return mine, idx, val

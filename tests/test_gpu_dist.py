@@ -1,0 +1,83 @@
+"""Row-partitioned training on 2 GPUs (NCCL) against the single-GPU path.  Needs >= 2 devices:
+run with `gpurun --gpus 2`; skipped on the 1-GPU round-end box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "tiny_ref.npz")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from furusato_recommend_b200 import LightGCN
+    from furusato_recommend_b200.dataloader import BasicDataset
+    from furusato_recommend_b200.parallel import DistLightGCN
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        g = dict(np.load(GOLD))
+        d, K, B = (int(x) for x in g["config"])
+        lr, decay = (float(x) for x in g["hyper"])
+        cfg = dict(recdim=d, layer=K, lr=lr, decay=decay, bpr_batch_size=B, device=dev, test_u_batch_size=128)
+        ds = BasicDataset(int(g["n_users"]), int(g["m_items"]), g["train_user"], g["train_item"], g["test_user"],
+                          g["test_item"], config=cfg, device=dev)
+        E0 = torch.from_numpy(g["E0"]).to(dev)
+        dm = DistLightGCN(cfg, ds, rank, world)
+        dm.load_global_embedding(E0)
+        u, p, q = (torch.from_numpy(g[k]).to(dev) for k in ("batch_users", "batch_pos", "batch_neg"))
+        out = dm.computer_local()
+        light = dm.part.unshard(_gather(dm, out))
+        ref = torch.from_numpy(np.concatenate([g["computer_users"], g["computer_items"]])).to(dev)
+        e_prop = float((light - ref).abs().max() / ref.abs().max())
+        l1 = float(dm.fused_step(u, p, q))
+        l2 = float(dm.fused_step(u, p, q))
+        E2 = dm.gather_embedding()
+        e_emb = float((E2.cpu() - torch.from_numpy(g["E2"])).abs().max())
+        users = torch.from_numpy(g["eval_users"]).to(dev)
+        dm.computer_local()
+        mine, idx, val = dm.topk_user_shard(users, 20, precision="fp32")
+        sm = LightGCN(cfg, ds)
+        with torch.no_grad():
+            sm.all_embedding.weight.copy_(E2)
+        sm.eval()
+        sidx, sval = sm.getUsersTopK(mine, 20, precision="fp32")
+        same = float((sidx == idx).float().mean())
+        ret[rank] = (e_prop, l1, l2, e_emb, same, float(g["step1_loss"]), float(g["step2_loss"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _gather(dm, local):
+    import torch.distributed as dist
+    full = torch.empty((dm.world * dm.part.R, dm.d), dtype=torch.float32, device=dm.device)
+    dist.all_gather_into_tensor(full, local)
+    return full
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_row_partitioned_training_matches_reference_2gpu():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        for rank in range(world):
+            e_prop, l1, l2, e_emb, same, g1, g2 = ret[rank]
+            assert e_prop < 1e-5, e_prop
+            assert abs(l1 - g1) < 1e-5 * g1 and abs(l2 - g2) < 1e-5 * g2, (l1, g1, l2, g2)
+            assert e_emb < 1e-6, e_emb
+            assert same > 0.999, same
+        assert ret[0][1] == ret[1][1]  # the loss is identical on every rank
