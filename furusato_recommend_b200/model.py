@@ -133,6 +133,9 @@ class LightGCN(nn.Module):
         self._g_clean = True
         self._seed_generation = 0
         self._eval_cache_valid = False
+        self.use_cuda_graph = bool(config.get("cuda_graph", True))
+        self._graph = None
+        self._graph_key = None
 
     def train(self, mode: bool = True):
         # weights only move in training mode; eval mode may reuse one propagation
@@ -251,20 +254,58 @@ class LightGCN(nn.Module):
         users, pos, neg = self._ids(users), self._ids(pos), self._ids(neg)
         return _BprFn.apply(self.all_embedding.weight, self, users, pos, neg)
 
-    def _ids(self, t) -> torch.Tensor:
+    def _ids(self, t, keep_host: bool = False) -> torch.Tensor:
         if not torch.is_tensor(t):
             t = torch.as_tensor(t)
+        if keep_host and not t.is_cuda and self.use_cuda_graph and t.numel() == int(self.config["bpr_batch_size"]):
+            return t.to(torch.int64).contiguous()   # copied straight into the graph's static batch buffers
         return t.to(device=self.all_embedding.weight.device, dtype=torch.int64).contiguous()
 
     @torch.no_grad()
     def stageOne(self, user, pos, neg) -> torch.Tensor:
         """model/lgcn.py:127-133 as one fused step: zero_grad + bpr_loss +
         decay*reg + backward + Adam.  Returns loss + decay*reg (0-dim tensor)."""
-        users, pos, neg = self._ids(user), self._ids(pos), self._ids(neg)
-        self._fused_step(users, pos, neg)
+        self._fused_step(self._ids(user, keep_host=True), self._ids(pos, keep_host=True),
+                         self._ids(neg, keep_host=True))
         return self._buf("loss_out")[2].clone()
 
     def _fused_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> None:
+        """One fused train step.  Full-size batches replay a captured CUDA graph (8 kernels, no
+        per-launch host work); anything else (last partial batch, cuda_graph=False) launches eagerly."""
+        B = users.numel()
+        if not self.use_cuda_graph or B != int(self.config["bpr_batch_size"]):
+            return self._fused_step_eager(self._ids(users), self._ids(pos), self._ids(neg))
+        self._reset_seed_buffers()  # only dirty after the autograd path; the graph assumes clean G/cnt
+        lr = self.optim.param_groups[0]["lr"]
+        if self._graph is None or self._graph_key != (B, lr, float(self.config["decay"]), self.num_layers):
+            self._capture_step_graph(B)
+        for dst, src in zip(self._gbatch, (users, pos, neg)):
+            dst.copy_(src, non_blocking=True)      # device slice or pinned host memory
+        self._graph.replay()
+        self._eval_cache_valid = False
+
+    def _capture_step_graph(self, B: int) -> None:
+        dev = self.all_embedding.weight.device
+        self._gbatch = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(3)]
+        st = self.optim._init_state(self.all_embedding.weight)
+        # the warm-up step below must not move the model: snapshot and restore every mutable buffer
+        keep = [t.clone() for t in (self.all_embedding.weight.data, st["exp_avg"], st["exp_avg_sq"], st["step"], st["hp"],
+                                    self._buf("loss_out"))]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._fused_step_eager(*self._gbatch)   # allocates every lazily created buffer
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._fused_step_eager(*self._gbatch)
+        for t, k in zip((self.all_embedding.weight.data, st["exp_avg"], st["exp_avg_sq"], st["step"], st["hp"],
+                         self._buf("loss_out")), keep):
+            t.copy_(k)
+        self._graph = graph
+        self._graph_key = (B, self.optim.param_groups[0]["lr"], float(self.config["decay"]), self.num_layers)
+
+    def _fused_step_eager(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> None:
         w = self.all_embedding.weight
         B = users.numel()
         group = self.optim.param_groups[0]

@@ -149,10 +149,10 @@ class DistPropagator:
 
 
 def exchange_rows(part: RowPartition, rank: int, local: torch.Tensor, padded_ids: torch.Tensor, group=None):
-    """rows[i] = TABLE[padded_ids[i]] where TABLE is row-partitioned: owners fill, one all-reduce."""
-    buf = torch.zeros((padded_ids.numel(), local.shape[1]), dtype=local.dtype, device=local.device)
+    """rows[i] = TABLE[padded_ids[i]] where TABLE is row-partitioned: owners fill, one all-reduce.
+    Sync-free (no boolean indexing): non-owners gather a valid dummy row and multiply it by 0."""
     mine = (padded_ids // part.R) == rank
-    buf[mine] = local[(padded_ids[mine] % part.R)]
+    buf = local[padded_ids % part.R] * mine[:, None].to(local.dtype)
     if part.world > 1:
         dist.all_reduce(buf, group=group)
     return buf, mine
@@ -190,7 +190,8 @@ class DistLightGCN:
         self.work_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         storage = torch.bfloat16 if config.get("storage_dtype") == "bf16" else torch.float32
         self.prop = DistPropagator(self.part, rank, dl, self.K, self._local_spmm, group, storage)
-        self.collectives_per_step = 2 * self.K + 2
+        self.collectives_per_step = 2 * self.K + 1
+        self._ar = None
 
     def load_global_embedding(self, E: torch.Tensor) -> None:
         """Take this rank's rows of a global [N, d] table (checkpoint key all_embedding.weight)."""
@@ -216,17 +217,23 @@ class DistLightGCN:
         ops, part, B = self.ops, self.part, users.numel()
         self.prop.forward(self.emb, self.acc, self.out)
         ids = part.to_padded(torch.cat([users, pos + self.n, neg + self.n]))
-        out_c, mine = exchange_rows(part, self.rank, self.out, ids, self.group)
-        emb_c, _ = exchange_rows(part, self.rank, self.emb, ids, self.group)
-        ar = torch.arange(B, device=self.device, dtype=torch.int64)
-        G_c = torch.zeros_like(out_c)
-        cnt_c = torch.zeros(3 * B, dtype=torch.int32, device=self.device)
-        work = torch.empty(2 * B, dtype=torch.float32, device=self.device)
+        # one all-reduce for both the propagated and the ego rows: [3B, 2d]
+        both, mine = exchange_rows(part, self.rank, torch.cat([self.out, self.emb], dim=1), ids, self.group)
+        out_c, emb_c = both[:, :self.d].contiguous(), both[:, self.d:].contiguous()
+        if self._ar is None or self._ar.numel() != B:
+            self._ar = torch.arange(B, device=self.device, dtype=torch.int64)
+            self._G_c = torch.empty((3 * B, self.d), dtype=torch.float32, device=self.device)
+            self._cnt_c = torch.empty(3 * B, dtype=torch.int32, device=self.device)
+            self._work = torch.empty(2 * B, dtype=torch.float32, device=self.device)
+        ar, G_c, cnt_c = self._ar, self._G_c, self._cnt_c
+        G_c.zero_()
+        cnt_c.zero_()
         decay = float(self.config["decay"])
-        ops.bpr_fwd_bwd(out_c, emb_c, ar, ar, ar + B, B, decay, G_c, cnt_c, self.loss_out, work, self.work_counter)
-        loc = ids[mine] % part.R
-        self.G.index_add_(0, loc, G_c[mine])
-        self.cnt.index_add_(0, loc, cnt_c[mine])
+        ops.bpr_fwd_bwd(out_c, emb_c, ar, ar, ar + B, B, decay, G_c, cnt_c, self.loss_out, self._work,
+                        self.work_counter)
+        loc = ids % part.R                      # owners add their rows, everyone else adds zeros to a valid row
+        self.G.index_add_(0, loc, G_c * mine[:, None].to(G_c.dtype))
+        self.cnt.index_add_(0, loc, cnt_c * mine.to(cnt_c.dtype))
         ops.adam_tick(self.step_t, self.hp, float(self.config["lr"]))
         self.prop.backward(self.G, grad_mode=2, inv_layers=1.0 / (self.K + 1), reg_coef=decay / B, cnt=self.cnt,
                            emb=self.emb, adam_m=self.m1, adam_v=self.v1, adam_hp=self.hp, zero_base=False)
