@@ -6,10 +6,11 @@ There is NO fallback: if the library is missing or an entry point fails, a
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "liblgcn_b200.so"
+LIB_PATH = Path(os.environ.get("LGCN_B200_LIB", PKG / "liblgcn_b200.so"))  # override: tuning variants
 
 ABI_VERSION = 1
 F32, BF16 = 0, 1
@@ -28,7 +29,7 @@ class GraphStruct(C.Structure):
     _fields_ = [
         ("n_nodes", C.c_int64), ("nnz", C.c_int64),
         ("rowptr", C.c_void_p), ("col", C.c_void_p), ("dinv", C.c_void_p),
-        ("light_rows", C.c_void_p), ("n_light", C.c_int64),
+        ("light_desc", C.c_void_p), ("n_light", C.c_int64),
         ("seg_row", C.c_void_p), ("seg_begin", C.c_void_p), ("seg_len", C.c_void_p),
         ("seg_hub", C.c_void_p), ("n_seg", C.c_int64),
         ("hub_seg0", C.c_void_p), ("hub_nseg", C.c_void_p), ("hub_counter", C.c_void_p),

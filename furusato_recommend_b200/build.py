@@ -40,6 +40,20 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(tag: str, defines: dict) -> Path:
+    """Tuning aid: liblgcn_b200_<tag>.so with -D overrides (select it with LGCN_B200_LIB)."""
+    out = PKG / f"liblgcn_b200_{tag}.so"
+    objs = []
+    for src in SOURCES:
+        obj = CSRC / f"{src[:-3]}_{tag}.o"
+        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in defines.items()], "-c", str(CSRC / src), "-o", str(obj)]
+        subprocess.run(cmd, check=True)
+        objs.append(str(obj))
+    subprocess.run([_nvcc(), "-shared", "-o", str(out), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-Xcompiler", "-fPIC", "-lcudart_static", "-ldl", "-lrt", "-lpthread"], check=True)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     digest = _digest()
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:

@@ -17,7 +17,9 @@
 //     memory in a fixed order, and multi-segment hubs are finished by the last
 //     arriving CTA which adds the partials in segment order (deterministic);
 //   * light rows are visited in degree-descending order so the longest chains
-//     start first and the tail of the grid is made of cheap rows.
+//     start first and the tail of the grid is made of cheap rows; each has a packed
+//     16-byte descriptor {row, degree, first edge} so the chain is descriptor ->
+//     column ids -> neighbour rows, with the epilogue operands prefetched up front.
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -35,6 +37,12 @@ void set_last_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 
 constexpr int kBlock = 256;
+#ifndef LGCN_SPMM_UNROLL
+#define LGCN_SPMM_UNROLL 4
+#endif
+#ifndef LGCN_SPMM_MINBLOCKS
+#define LGCN_SPMM_MINBLOCKS 4
+#endif
 
 template <int D, bool SRC_BF16>
 struct RowCfg {
@@ -42,7 +50,7 @@ struct RowCfg {
   static constexpr int kLPR = kRowBytes / 16;          // lanes per row
   static constexpr int kEPL = SRC_BF16 ? 8 : 4;        // elements per lane
   static constexpr int kGroups = kBlock / kLPR;        // groups per CTA
-  static constexpr int kUnroll = kLPR >= 8 ? 8 : kLPR; // neighbour rows in flight
+  static constexpr int kUnroll = kLPR >= LGCN_SPMM_UNROLL ? LGCN_SPMM_UNROLL : kLPR; // neighbour rows in flight
   static_assert(kRowBytes % 16 == 0 && kLPR >= 2 && kLPR <= 32, "unsupported row width");
   static_assert((kLPR & (kLPR - 1)) == 0, "lanes per row must be a power of two");
 };
@@ -51,7 +59,7 @@ struct GraphDev {
   const int64_t* rowptr;
   const int32_t* col;
   const float* dinv;
-  const int32_t* light_rows;
+  const int4* light_desc;
   int64_t n_light;
   const int32_t* seg_row;
   const int64_t* seg_begin;
@@ -148,11 +156,34 @@ __device__ __forceinline__ void gather_sum(const void* __restrict__ src,
 }
 
 // Row epilogue; lane `lig` holds s[0..EPL) = elements [lig*EPL, lig*EPL+EPL) of row.
+// Operands of the row epilogue that do not depend on the gather: fetched BEFORE it so their
+// latency hides behind the neighbour loads instead of extending the per-row dependency chain.
+template <int EPL>
+struct RowPre {
+  float di;
+  float v[EPL];  // base[row] (backward) or acc_in[row] (forward)
+};
+
+template <int D, int EPL>
+__device__ __forceinline__ RowPre<EPL> row_prefetch(const EpiDev& p, const float* __restrict__ dinv,
+                                                    int64_t row, int lig) {
+  RowPre<EPL> r;
+  r.di = __ldg(dinv + row);
+  const float* src = p.base != nullptr ? p.base : p.acc_in;
+  const int64_t off = row * D + lig * EPL;
+#pragma unroll
+  for (int q = 0; q < EPL / 4; ++q) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src != nullptr) b = ld_f4(src + off + 4 * q);
+    r.v[4 * q + 0] = b.x; r.v[4 * q + 1] = b.y; r.v[4 * q + 2] = b.z; r.v[4 * q + 3] = b.w;
+  }
+  return r;
+}
+
 template <int D, int EPL, bool DST_BF16>
-__device__ __forceinline__ void row_epilogue(const EpiDev& p, const float* __restrict__ dinv,
-                                             int64_t row, int lig, unsigned gmask,
-                                             const float (&s)[EPL]) {
-  const float di = __ldg(dinv + row);
+__device__ __forceinline__ void row_epilogue(const EpiDev& p, const RowPre<EPL>& pre, int64_t row,
+                                             int lig, unsigned gmask, const float (&s)[EPL]) {
+  const float di = pre.di;
   const int64_t off = row * D + lig * EPL;
   float x[EPL], t[EPL];
 #pragma unroll
@@ -160,13 +191,7 @@ __device__ __forceinline__ void row_epilogue(const EpiDev& p, const float* __res
 
   if (p.base != nullptr) {
 #pragma unroll
-    for (int q = 0; q < EPL / 4; ++q) {
-      const float4 b = ld_f4(p.base + off + 4 * q);
-      t[4 * q + 0] = b.x + x[4 * q + 0];
-      t[4 * q + 1] = b.y + x[4 * q + 1];
-      t[4 * q + 2] = b.z + x[4 * q + 2];
-      t[4 * q + 3] = b.w + x[4 * q + 3];
-    }
+    for (int j = 0; j < EPL; ++j) t[j] = pre.v[j] + x[j];
   } else {
 #pragma unroll
     for (int j = 0; j < EPL; ++j) t[j] = x[j];
@@ -197,14 +222,14 @@ __device__ __forceinline__ void row_epilogue(const EpiDev& p, const float* __res
     }
   }
 
-  if (p.acc_out != nullptr) {
+  if (p.acc_out != nullptr) {  // base == nullptr on this path, so pre.v holds acc_in[row]
 #pragma unroll
-    for (int q = 0; q < EPL / 4; ++q) {
-      const float4 a = ld_f4(p.acc_in + off + 4 * q);
+    for (int q = 0; q < EPL / 4; ++q)
       st_f4(p.acc_out + off + 4 * q,
-            make_float4((a.x + x[4 * q + 0]) * p.acc_scale, (a.y + x[4 * q + 1]) * p.acc_scale,
-                        (a.z + x[4 * q + 2]) * p.acc_scale, (a.w + x[4 * q + 3]) * p.acc_scale));
-    }
+            make_float4((pre.v[4 * q + 0] + x[4 * q + 0]) * p.acc_scale,
+                        (pre.v[4 * q + 1] + x[4 * q + 1]) * p.acc_scale,
+                        (pre.v[4 * q + 2] + x[4 * q + 2]) * p.acc_scale,
+                        (pre.v[4 * q + 3] + x[4 * q + 3]) * p.acc_scale));
   }
 
   if (p.grad_mode != 0) {
@@ -251,7 +276,8 @@ __device__ __forceinline__ void row_epilogue(const EpiDev& p, const float* __res
 }
 
 template <int D, bool SRC_BF16, bool DST_BF16, bool SCALE_SRC>
-__global__ void __launch_bounds__(kBlock) spmm_layer_kernel(const GraphDev g, const EpiDev p) {
+__global__ void __launch_bounds__(kBlock, LGCN_SPMM_MINBLOCKS)
+spmm_layer_kernel(const GraphDev g, const EpiDev p) {
   using C = RowCfg<D, SRC_BF16>;
   constexpr int LPR = C::kLPR, EPL = C::kEPL, NG = C::kGroups;
   const int lig = threadIdx.x % LPR;   // lane in group
@@ -266,10 +292,12 @@ __global__ void __launch_bounds__(kBlock) spmm_layer_kernel(const GraphDev g, co
     // ---------------- light rows: one group per row ----------------
     const int64_t gid = (int64_t)(blockIdx.x - g.n_seg) * NG + grp;
     if (gid >= g.n_light) return;
-    const int64_t row = g.light_rows[gid];
-    const int64_t b = g.rowptr[row], e = g.rowptr[row + 1];
-    gather_sum<D, SRC_BF16, SCALE_SRC>(p.src, g.col, g.dinv, b, e, LPR, lig, gmask, acc);
-    row_epilogue<D, EPL, DST_BF16>(p, g.dinv, row, lig, gmask, acc);
+    const int4 dsc = __ldg(g.light_desc + gid);  // {row, degree, first edge lo, hi}: one hop, no rowptr
+    const int64_t row = dsc.x;
+    const int64_t b = (int64_t)(((uint64_t)(uint32_t)dsc.w << 32) | (uint32_t)dsc.z);
+    const RowPre<EPL> pre = row_prefetch<D, EPL>(p, g.dinv, row, lig);
+    gather_sum<D, SRC_BF16, SCALE_SRC>(p.src, g.col, g.dinv, b, b + dsc.y, LPR, lig, gmask, acc);
+    row_epilogue<D, EPL, DST_BF16>(p, pre, row, lig, gmask, acc);
     return;
   }
 
@@ -318,7 +346,8 @@ __global__ void __launch_bounds__(kBlock) spmm_layer_kernel(const GraphDev g, co
     float s[EPL];
 #pragma unroll
     for (int j = 0; j < EPL; ++j) s[j] = red[0][lig * EPL + j];
-    row_epilogue<D, EPL, DST_BF16>(p, g.dinv, row, lig, gmask, s);
+    const RowPre<EPL> pre = row_prefetch<D, EPL>(p, g.dinv, row, lig);
+    row_epilogue<D, EPL, DST_BF16>(p, pre, row, lig, gmask, s);
   }
 }
 
@@ -386,7 +415,7 @@ extern "C" int lgcn_propagate_layer(const lgcn_graph_t* gh, const lgcn_layer_arg
 
   GraphDev g;
   g.rowptr = gh->rowptr; g.col = gh->col; g.dinv = gh->dinv;
-  g.light_rows = gh->light_rows; g.n_light = gh->n_light;
+  g.light_desc = reinterpret_cast<const int4*>(gh->light_desc); g.n_light = gh->n_light;
   g.seg_row = gh->seg_row; g.seg_begin = gh->seg_begin; g.seg_len = gh->seg_len;
   g.seg_hub = gh->seg_hub; g.n_seg = (int)gh->n_seg;
   g.hub_seg0 = gh->hub_seg0; g.hub_nseg = gh->hub_nseg; g.hub_counter = gh->hub_counter;

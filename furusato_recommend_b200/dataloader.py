@@ -160,6 +160,45 @@ class BasicDataset:
         return self.testUser[np.sort(first)]
 
 
+class DeviceDataset(BasicDataset):
+    """Same contract, but the interactions live on the GPU and never visit the host (cfg-3-sized
+    graphs: 500 M edges).  Host-side views (`allPos`, `testDict`, `trainUser`) are materialised
+    lazily and only make sense for small cases."""
+
+    def __init__(self, n_users: int, m_items: int, train_user: torch.Tensor, train_item: torch.Tensor,
+                 test_user: torch.Tensor, test_item: torch.Tensor, config: Optional[dict] = None):
+        self.config = dict(config or {})
+        self.n_user, self.m_item = int(n_users), int(m_items)
+        self._tu, self._ti, self._su, self._si = train_user, train_item, test_user, test_item
+        self.traindataSize, self.testDataSize = int(train_user.numel()), int(test_user.numel())
+        self.split = bool(self.config.get("A_split", False))
+        self.folds = int(self.config.get("A_n_fold", 1))
+        self.device = train_user.device
+        self.Graph = None
+        self._csr = self._pos_dev = self._test_dev = self._allPos = self._testDict = None
+
+    trainUser = property(lambda self: self._tu.cpu().numpy())
+    trainItem = property(lambda self: self._ti.cpu().numpy())
+    testUser = property(lambda self: self._su.cpu().numpy())
+    testItem = property(lambda self: self._si.cpu().numpy())
+
+    def csr_graph(self) -> CsrGraph:
+        if self._csr is None:
+            self._csr = build_csr_graph(self.n_user, self.m_item, self._tu, self._ti)
+        return self._csr
+
+    def pos_csr(self):
+        if self._pos_dev is None:
+            self._pos_dev = build_pos_csr(self.n_user, self._tu, self._ti)
+        return self._pos_dev
+
+    def test_csr(self):
+        if self._test_dev is None:
+            rp, _, srt = build_pos_csr(self.n_user, self._su, self._si)
+            self._test_dev = (rp, srt)
+        return self._test_dev
+
+
 class Loader(BasicDataset):
     """`Loader(config, path)`: parses `{path}/{suffix}/train{suffix}.txt` and
     `test{suffix}.txt` ("uid item item ..." per line, dataloader.py:93-150).

@@ -26,6 +26,7 @@ class CsrGraph:
     col: torch.Tensor         # int32 [nnz]
     dinv: torch.Tensor        # fp32  [N]
     light_rows: torch.Tensor  # int32 [n_light], degree-descending
+    light_desc: torch.Tensor  # int32 [n_light, 4] = {row, degree, first edge lo, hi}
     seg_row: torch.Tensor     # int32 [n_seg]
     seg_begin: torch.Tensor   # int64 [n_seg]
     seg_len: torch.Tensor     # int32 [n_seg]
@@ -50,7 +51,7 @@ class CsrGraph:
 
     def to(self, device) -> "CsrGraph":
         kw = {}
-        for f in ("rowptr", "col", "dinv", "light_rows", "seg_row", "seg_begin", "seg_len",
+        for f in ("rowptr", "col", "dinv", "light_rows", "light_desc", "seg_row", "seg_begin", "seg_len",
                   "seg_hub", "hub_seg0", "hub_nseg", "hub_counter"):
             kw[f] = getattr(self, f).to(device)
         return CsrGraph(self.n_users, self.m_items, **kw)
@@ -65,7 +66,7 @@ class CsrGraph:
             s = _lib.GraphStruct()
             s.n_nodes, s.nnz = self.n_nodes, self.nnz
             s.rowptr, s.col, s.dinv = self.rowptr.data_ptr(), self.col.data_ptr(), self.dinv.data_ptr()
-            s.light_rows, s.n_light = self.light_rows.data_ptr(), int(self.light_rows.numel())
+            s.light_desc, s.n_light = self.light_desc.data_ptr(), int(self.light_rows.numel())
             s.seg_row, s.seg_begin = self.seg_row.data_ptr(), self.seg_begin.data_ptr()
             s.seg_len, s.seg_hub = self.seg_len.data_ptr(), self.seg_hub.data_ptr()
             s.n_seg = int(self.seg_row.numel())
@@ -102,8 +103,14 @@ def decompose_rows(rowptr: torch.Tensor, hub_deg: int = _lib.HUB_DEG, seg_edges:
         seg_row = seg_hub.clone()
         seg_begin = seg_hub.clone()
         seg_len = seg_hub.clone()
+    lr64 = light_rows.to(torch.int64)
+    begin = rowptr[lr64]
+    light_desc = torch.stack([lr64, deg[lr64], begin & 0xFFFFFFFF, begin >> 32], dim=1)
+    # low word may exceed int31: wrap to the signed representation of the same 32 bits
+    light_desc = torch.where(light_desc >= 2 ** 31, light_desc - 2 ** 32, light_desc).to(torch.int32)
     return dict(
         light_rows=light_rows.contiguous(),
+        light_desc=light_desc.contiguous(),
         seg_row=seg_row.to(torch.int32).contiguous(),
         seg_begin=seg_begin.to(torch.int64).contiguous(),
         seg_len=seg_len.to(torch.int32).contiguous(),

@@ -58,7 +58,8 @@ typedef struct lgcn_graph {
   const int32_t* col;        /* [nnz] neighbour node ids, sorted inside a row  */
   const float* dinv;         /* [N] deg^-1/2 (fp32), 0 where deg == 0          */
   /* work decomposition (degree-descending so long rows start first) */
-  const int32_t* light_rows; /* [n_light] rows with deg <= LGCN_HUB_DEG        */
+  const int32_t* light_desc; /* [n_light][4] = {row, degree, first edge lo, hi}  */
+                             /* of the rows with deg <= LGCN_HUB_DEG, 16 B aligned */
   int64_t n_light;
   const int32_t* seg_row;    /* [n_seg] hub row of each CTA segment            */
   const int64_t* seg_begin;  /* [n_seg] first edge                             */

