@@ -376,7 +376,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         traffic = None
         tp = REPO / "profiles" / "spmm_traffic.json"
         if tp.exists():
-            traffic = json.loads(tp.read_text()).get(f"dram_bytes_per_launch_{args.storage}")
+            traffic = json.loads(tp.read_text()).get(f"{args.workload}_dram_bytes_per_launch_{args.storage}")
         ms = t_dev / args.steps * 1e3
         out = {
             "metric": METRIC, "value": nnz_total * K / (t_dev / args.steps), "unit": UNIT, "n_gpus": world,
