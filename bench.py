@@ -265,8 +265,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     def e2e_step(b):
         if world == 1:
             return model.stageOne(hu[b:b + B], hp[b:b + B], hn[b:b + B]).item()
-        du, dp, dn = (t[b:b + B].to(dev, non_blocking=True) for t in (hu, hp, hn))
-        return model.fused_step(du, dp, dn).item()
+        return model.fused_step(hu[b:b + B], hp[b:b + B], hn[b:b + B]).item()
 
     for i in range(3):
         e2e_step(0)

@@ -192,6 +192,8 @@ class DistLightGCN:
         self.prop = DistPropagator(self.part, rank, dl, self.K, self._local_spmm, group, storage)
         self.collectives_per_step = 2 * self.K + 1
         self._ar = None
+        self.use_cuda_graph = bool(config.get("cuda_graph", True))
+        self._graph = None
 
     def load_global_embedding(self, E: torch.Tensor) -> None:
         """Take this rank's rows of a global [N, d] table (checkpoint key all_embedding.weight)."""
@@ -213,7 +215,38 @@ class DistLightGCN:
         return self.out
 
     def fused_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
-        """One training step on the same B triples on every rank (global ids)."""
+        """One training step on the same B triples on every rank (global ids).  Full-size batches
+        replay a CUDA graph that holds the kernels, the glue ops AND the NCCL collectives."""
+        B = users.numel()
+        if not self.use_cuda_graph or B != int(self.config["bpr_batch_size"]):
+            return self._fused_step_eager(users, pos, neg)
+        if self._graph is None:
+            self._capture(B)
+        for dst, src in zip(self._gbatch, (users, pos, neg)):
+            dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self.loss_out[2]
+
+    def _capture(self, B: int) -> None:
+        dev = self.device
+        self._gbatch = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(3)]
+        state = (self.emb, self.m1, self.v1, self.step_t, self.hp, self.loss_out)
+        keep = [t.clone() for t in state]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):                      # NCCL channels and every lazy buffer exist before capture
+                self._fused_step_eager(*self._gbatch)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._fused_step_eager(*self._gbatch)
+        for t, k in zip(state, keep):
+            t.copy_(k)
+        self._graph = graph
+
+    def _fused_step_eager(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
         ops, part, B = self.ops, self.part, users.numel()
         self.prop.forward(self.emb, self.acc, self.out)
         ids = part.to_padded(torch.cat([users, pos + self.n, neg + self.n]))
