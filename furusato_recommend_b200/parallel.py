@@ -192,7 +192,8 @@ class DistLightGCN:
         self.prop = DistPropagator(self.part, rank, dl, self.K, self._local_spmm, group, storage)
         self.collectives_per_step = 2 * self.K + 1
         self._ar = None
-        self.use_cuda_graph = bool(config.get("cuda_graph", True))
+        # capturing NCCL collectives into a CUDA graph deadlocked on the 2-GPU box (round 1); opt-in only
+        self.use_cuda_graph = bool(config.get("dist_cuda_graph", False))
         self._graph = None
 
     def load_global_embedding(self, E: torch.Tensor) -> None:
