@@ -220,6 +220,7 @@ class DistLightGCN:
         replay a CUDA graph that holds the kernels, the glue ops AND the NCCL collectives."""
         B = users.numel()
         if not self.use_cuda_graph or B != int(self.config["bpr_batch_size"]):
+            users, pos, neg = (t.to(self.device, non_blocking=True) for t in (users, pos, neg))
             return self._fused_step_eager(users, pos, neg)
         if self._graph is None:
             self._capture(B)
