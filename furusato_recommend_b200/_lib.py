@@ -16,6 +16,7 @@ ABI_VERSION = 1
 F32, BF16 = 0, 1
 HUB_DEG = 256
 SEG_EDGES = 1024
+MAX_PEERS = 8
 ERR_INVALID_ARG = -1
 ERR_UNSUPPORTED = -2
 
@@ -48,6 +49,7 @@ class LayerArgs(C.Structure):
         ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("adam_hp", C.c_void_p),
         ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
         ("zero_base", C.c_int),
+        ("n_dst_peers", C.c_int), ("dst_row_offset", C.c_int64), ("dst_peers", C.c_void_p * MAX_PEERS),
     ]
 
 
@@ -57,6 +59,7 @@ SIGNATURES = {
     "lgcn_abi_version": (C.c_int, []),
     "lgcn_last_error": (C.c_char_p, []),
     "lgcn_propagate_layer": (C.c_int, [C.POINTER(GraphStruct), C.POINTER(LayerArgs), _P]),
+    "lgcn_scale_rows_push": (C.c_int, [_P, _P, _I64, _I, _I, C.POINTER(C.c_void_p), _I, _I64, _P]),
     "lgcn_bpr_fwd_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
     "lgcn_adam_tick": (C.c_int, [_P, _P, _D, _D, _D, _P]),
     "lgcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, _D, _D, _D, _P]),

@@ -90,6 +90,9 @@ struct EpiDev {
   const float* adam_hp;
   float one_minus_b1, beta2, one_minus_b2, eps;
   int zero_base;
+  int n_peer;
+  int64_t dst_row_off;
+  void* peer[LGCN_MAX_PEERS];
 };
 
 // Sum of w_j * SRC[col[e]] over e = e0, e0+1, .. inside [e0, e_end) taken in
@@ -201,24 +204,31 @@ __device__ __forceinline__ void row_epilogue(const EpiDev& p, const RowPre<EPL>&
     float z[EPL];
 #pragma unroll
     for (int j = 0; j < EPL; ++j) z[j] = di * t[j];
-    if (DST_BF16) {
-      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.dst) + off;
-      if (EPL == 8) {
-        float z8[8];
+    // n_peer == 0: plain local store.  n_peer > 0: the all-gather is fused here — the row goes to
+    // every rank's gathered buffer over NVLink (peer-mapped pointers), at this rank's row block.
+    const int n_dst = p.n_peer > 0 ? p.n_peer : 1;
+    const int64_t doff = p.n_peer > 0 ? (p.dst_row_off + row) * D + lig * EPL : off;
+    for (int q = 0; q < n_dst; ++q) {
+      void* base_ptr = p.n_peer > 0 ? p.peer[q] : p.dst;
+      if (DST_BF16) {
+        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(base_ptr) + doff;
+        if (EPL == 8) {
+          float z8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z8[j] = z[j % EPL];
-        st_u4(dp, pack_bf16x8(z8));
+          for (int j = 0; j < 8; ++j) z8[j] = z[j % EPL];
+          st_u4(dp, pack_bf16x8(z8));
+        } else {
+          uint2 w2;
+          w2.x = pack_bf16x2(z[0], z[1]);
+          w2.y = pack_bf16x2(z[2], z[3]);
+          *reinterpret_cast<uint2*>(dp) = w2;
+        }
       } else {
-        uint2 w2;
-        w2.x = pack_bf16x2(z[0], z[1]);
-        w2.y = pack_bf16x2(z[2], z[3]);
-        *reinterpret_cast<uint2*>(dp) = w2;
-      }
-    } else {
-      float* dp = reinterpret_cast<float*>(p.dst) + off;
+        float* dp = reinterpret_cast<float*>(base_ptr) + doff;
 #pragma unroll
-      for (int q = 0; q < EPL / 4; ++q)
-        st_f4(dp + 4 * q, make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]));
+        for (int qq = 0; qq < EPL / 4; ++qq)
+          st_f4(dp + 4 * qq, make_float4(z[4 * qq], z[4 * qq + 1], z[4 * qq + 2], z[4 * qq + 3]));
+      }
     }
   }
 
@@ -394,6 +404,55 @@ static int dispatch_dtype(const lgcn_layer_args_t* a, const GraphDev& g, const E
 
 using namespace lgcn;
 
+namespace lgcn {
+struct PeerPtrs { void* p[LGCN_MAX_PEERS]; };
+
+template <bool DST_BF16>
+__global__ void __launch_bounds__(256)
+scale_rows_push_kernel(const float* __restrict__ x, const float* __restrict__ dinv, int64_t n_vec, int d4,
+                       PeerPtrs peers, int n_peer, int64_t dst_elem_off) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / d4;
+    const float di = __ldg(dinv + row);
+    const float4 v = ld_f4(x + 4 * i);
+    const float z0 = di * v.x, z1 = di * v.y, z2 = di * v.z, z3 = di * v.w;
+    for (int q = 0; q < n_peer; ++q) {
+      if (DST_BF16) {
+        uint2 w2;
+        w2.x = pack_bf16x2(z0, z1);
+        w2.y = pack_bf16x2(z2, z3);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(peers.p[q]) + dst_elem_off + 4 * i) = w2;
+      } else {
+        st_f4(reinterpret_cast<float*>(peers.p[q]) + dst_elem_off + 4 * i, make_float4(z0, z1, z2, z3));
+      }
+    }
+  }
+}
+}  // namespace lgcn
+
+extern "C" int lgcn_scale_rows_push(const float* x, const float* dinv, int64_t n_rows, int d, int dst_dtype,
+                                    void* const* dst_peers, int n_dst_peers, int64_t dst_row_offset,
+                                    lgcn_stream_t stream) {
+  LGCN_CHECK_ARG(x && dinv && dst_peers, "null pointer argument");
+  LGCN_CHECK_ARG(n_dst_peers >= 1 && n_dst_peers <= LGCN_MAX_PEERS, "n_dst_peers out of range");
+  LGCN_CHECK_ARG(d > 0 && d % 4 == 0 && n_rows >= 0, "bad shape");
+  if (n_rows == 0) return 0;
+  lgcn::PeerPtrs pp;
+  for (int q = 0; q < LGCN_MAX_PEERS; ++q) pp.p[q] = q < n_dst_peers ? dst_peers[q] : nullptr;
+  const int64_t n_vec = n_rows * (d / 4);
+  int64_t blocks = (n_vec + 255) / 256;
+  if (blocks > (int64_t)lgcn::kSmCount * 16) blocks = (int64_t)lgcn::kSmCount * 16;
+  if (dst_dtype == LGCN_BF16)
+    lgcn::scale_rows_push_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        x, dinv, n_vec, d / 4, pp, n_dst_peers, dst_row_offset * d);
+  else
+    lgcn::scale_rows_push_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        x, dinv, n_vec, d / 4, pp, n_dst_peers, dst_row_offset * d);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int lgcn_abi_version(void) { return LGCN_ABI_VERSION; }
 extern "C" const char* lgcn_last_error(void) { return lgcn::last_error(); }
 
@@ -432,6 +491,10 @@ extern "C" int lgcn_propagate_layer(const lgcn_graph_t* gh, const lgcn_layer_arg
   p.one_minus_b2 = (float)(1.0 - a->beta2);
   p.eps = (float)a->eps;
   p.zero_base = a->zero_base;
+  LGCN_CHECK_ARG(a->n_dst_peers >= 0 && a->n_dst_peers <= LGCN_MAX_PEERS, "n_dst_peers out of range");
+  p.n_peer = a->n_dst_peers;
+  p.dst_row_off = a->dst_row_offset;
+  for (int q = 0; q < LGCN_MAX_PEERS; ++q) p.peer[q] = q < a->n_dst_peers ? a->dst_peers[q] : nullptr;
   LGCN_CHECK_ARG(!(a->zero_base && a->base == a->src), "zero_base with src == base races");
 
   cudaStream_t st = (cudaStream_t)stream;

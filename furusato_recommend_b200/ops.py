@@ -48,7 +48,8 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
                     cnt: Optional[torch.Tensor] = None, emb: Optional[torch.Tensor] = None,
                     grad: Optional[torch.Tensor] = None, adam_m: Optional[torch.Tensor] = None,
                     adam_v: Optional[torch.Tensor] = None, adam_hp: Optional[torch.Tensor] = None,
-                    betas=(0.9, 0.999), eps: float = 1e-8, zero_base: bool = False) -> None:
+                    betas=(0.9, 0.999), eps: float = 1e-8, zero_base: bool = False,
+                    dst_peers: Optional[Sequence[int]] = None, dst_row_offset: int = 0) -> None:
     """lgcn_propagate_layer: one normalised-adjacency SpMM + fused row epilogue."""
     lib = _lib.load()
     n_src, d = src.shape
@@ -73,11 +74,28 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
     a.adam_hp = _chk(adam_hp, torch.float32, "adam_hp", True)
     a.beta1, a.beta2, a.eps = betas[0], betas[1], eps
     a.zero_base = int(zero_base)
-    for t, nm in ((dst, "dst"), (base, "base"), (acc_in, "acc_in"), (acc_out, "acc_out"), (emb, "emb"),
+    if dst_peers:
+        if dst is None:
+            raise ValueError("dst_peers needs dst (it fixes the dtype and enables the write)")
+        a.n_dst_peers, a.dst_row_offset = len(dst_peers), dst_row_offset
+        for i, ptr in enumerate(dst_peers):
+            a.dst_peers[i] = ptr
+    for t, nm in ((None if dst_peers else dst, "dst"), (base, "base"), (acc_in, "acc_in"), (acc_out, "acc_out"), (emb, "emb"),
                   (grad, "grad"), (adam_m, "adam_m"), (adam_v, "adam_v")):
         if t is not None and tuple(t.shape) != (N, d):
             raise ValueError(f"{nm} must be [{N}, {d}], got {tuple(t.shape)}")
     _lib.check(lib.lgcn_propagate_layer(C.byref(g.c_struct(d)), C.byref(a), _stream()), "lgcn_propagate_layer")
+
+
+def scale_rows_push(x: torch.Tensor, dinv: torch.Tensor, dst_dtype: torch.dtype, dst_peers: Sequence[int],
+                    dst_row_offset: int) -> None:
+    """dst_p[row_offset + i] = dinv[i] * x[i] on every peer buffer (pre-scaled first-layer source)."""
+    lib = _lib.load()
+    n, d = x.shape
+    arr = (C.c_void_p * len(dst_peers))(*dst_peers)
+    _lib.check(lib.lgcn_scale_rows_push(_chk(x, torch.float32, "x"), _chk(dinv, torch.float32, "dinv"), n, d,
+                                        _lib.BF16 if dst_dtype == torch.bfloat16 else _lib.F32, arr, len(dst_peers),
+                                        dst_row_offset, _stream()), "lgcn_scale_rows_push")
 
 
 def bpr_fwd_bwd(out: torch.Tensor, emb: torch.Tensor, users: torch.Tensor, pos: torch.Tensor,

@@ -148,6 +148,55 @@ class DistPropagator:
             src = z[j & 1]
 
 
+class PushPropagator:
+    """Same maths as DistPropagator, but the per-layer all-gather is FUSED into the producing
+    kernel: the SpMM epilogue stores every pre-scaled output row straight into all ranks'
+    gathered buffers through NVLink peer mappings (torch symmetric memory supplies the mapped
+    pointers and the cross-GPU barrier).  No NCCL call and no staging copy on the layer path;
+    the transfer overlaps the gather/FMA work of the same kernel row by row.
+
+    Two symmetric [W*R, d] buffers ping-pong: layer k reads buf[k&1] and pushes into buf[(k+1)&1]
+    of every peer; one barrier per layer separates the writers of a buffer from its readers."""
+
+    def __init__(self, part: RowPartition, rank: int, graph, dinv_local: torch.Tensor, n_layers: int,
+                 ops, group, d: int, storage_dtype: torch.dtype, device):
+        import torch.distributed._symmetric_memory as symm
+        self.part, self.rank, self.K, self.ops, self.graph = part, rank, n_layers, ops, graph
+        self.dinv, self.storage_dtype = dinv_local, storage_dtype
+        R, W = part.R, part.world
+        self.bufs = [symm.empty((W * R, d), dtype=storage_dtype, device=device) for _ in range(2)]
+        self.hdl = [symm.rendezvous(t, group) for t in self.bufs]
+        self.peers = [[int(p) for p in h.buffer_ptrs] for h in self.hdl]
+        self.row0 = rank * R
+
+    def _barrier(self):
+        self.hdl[0].barrier(channel=0)
+
+    def _run(self, first_src: torch.Tensor, layer_kwargs):
+        ops, K = self.ops, self.K
+        self._barrier()  # every peer is done reading buf[0] (last layer of the previous pass)
+        ops.scale_rows_push(first_src, self.dinv, self.storage_dtype, self.peers[0], self.row0)
+        self._barrier()
+        for k in range(K):
+            last = k == K - 1
+            nxt = (k + 1) & 1
+            ops.propagate_layer(self.graph, self.bufs[k & 1], scale_src=False,
+                                dst=None if last else self.bufs[nxt],
+                                dst_peers=None if last else self.peers[nxt], dst_row_offset=self.row0,
+                                **layer_kwargs(k, last))
+            if not last:
+                self._barrier()
+
+    def forward(self, emb_local: torch.Tensor, acc: torch.Tensor, out: torch.Tensor) -> None:
+        K = self.K
+        self._run(emb_local, lambda k, last: dict(
+            acc_in=emb_local if k == 0 else acc, acc_out=out if last else acc,
+            acc_scale=1.0 / (K + 1) if last else 1.0))
+
+    def backward(self, G_local: torch.Tensor, **last_kwargs) -> None:
+        self._run(G_local, lambda k, last: dict(base=G_local, **(last_kwargs if last else {})))
+
+
 def exchange_rows(part: RowPartition, rank: int, local: torch.Tensor, padded_ids: torch.Tensor, group=None):
     """rows[i] = TABLE[padded_ids[i]] where TABLE is row-partitioned: owners fill, one all-reduce.
     Sync-free (no boolean indexing): non-owners gather a valid dummy row and multiply it by 0."""
@@ -189,7 +238,23 @@ class DistLightGCN:
         self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)
         self.work_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         storage = torch.bfloat16 if config.get("storage_dtype") == "bf16" else torch.float32
-        self.prop = DistPropagator(self.part, rank, dl, self.K, self._local_spmm, group, storage)
+        # "push": all-gather fused into the SpMM epilogue over NVLink peer memory (default when the
+        # ranks can map each other's memory); "nccl": ncclAllGather per layer (the baseline).
+        mode = config.get("dist_exchange", "auto")
+        self.exchange = "nccl"
+        self.prop = None
+        if world > 1 and mode in ("auto", "push"):
+            try:
+                self.prop = PushPropagator(self.part, rank, self.local_graph, dl, self.K, ops,
+                                           group if group is not None else dist.group.WORLD, d, storage, dev)
+                self.exchange = "push"
+            except Exception as e:  # no P2P / symmetric memory on this box
+                if mode == "push":
+                    raise
+                import warnings
+                warnings.warn(f"symmetric-memory push exchange unavailable ({e!r}); using NCCL all-gather")
+        if self.prop is None:
+            self.prop = DistPropagator(self.part, rank, dl, self.K, self._local_spmm, group, storage)
         self.collectives_per_step = 2 * self.K + 1
         self._ar = None
         # capturing NCCL collectives into a CUDA graph deadlocked on the 2-GPU box (round 1); opt-in only

@@ -39,6 +39,7 @@ extern "C" {
  * most LGCN_SEG_EDGES edges (host side builds the lists, see graph.py) */
 #define LGCN_HUB_DEG 256
 #define LGCN_SEG_EDGES 1024
+#define LGCN_MAX_PEERS 8
 
 typedef void* lgcn_stream_t; /* cudaStream_t */
 
@@ -115,10 +116,22 @@ typedef struct lgcn_layer_args {
   const float* adam_hp;/* device float[2]: {lr/bc1, sqrt(bc2)} (lgcn_adam_tick)  */
   double beta1, beta2, eps;
   int zero_base;       /* grad_mode 2: clear base[i] after use                  */
+  /* fused all-gather: when n_dst_peers > 0 the dst row is stored to EVERY peer buffer at
+   * row (dst_row_offset + i) instead of dst[i] (dst must still be non-NULL to enable the
+   * write).  The pointers are peer-mapped device memory (NVLink P2P / symmetric memory). */
+  int n_dst_peers;
+  int64_t dst_row_offset;
+  void* dst_peers[LGCN_MAX_PEERS];
 } lgcn_layer_args_t;
 
 int lgcn_propagate_layer(const lgcn_graph_t* g /*HOST*/, const lgcn_layer_args_t* a /*HOST*/,
                          lgcn_stream_t stream);
+
+/* dst_p[row_offset + i] = dinv[i] * x[i] on every peer p: the pre-scaled source of the first
+ * layer, pushed straight into the peers' gathered buffers (no separate all-gather). */
+int lgcn_scale_rows_push(const float* x, const float* dinv, int64_t n_rows, int d, int dst_dtype,
+                         void* const* dst_peers /*HOST array*/, int n_dst_peers,
+                         int64_t dst_row_offset, lgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Fused BPR forward + backward seed.  Replaces getEmbedding + bpr_loss

@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, exchange="auto"):
     import torch.distributed as dist
     from furusato_recommend_b200 import LightGCN
     from furusato_recommend_b200.dataloader import BasicDataset
@@ -32,7 +32,8 @@ def _worker(rank, world, port, ret):
         g = dict(np.load(GOLD))
         d, K, B = (int(x) for x in g["config"])
         lr, decay = (float(x) for x in g["hyper"])
-        cfg = dict(recdim=d, layer=K, lr=lr, decay=decay, bpr_batch_size=B, device=dev, test_u_batch_size=128)
+        cfg = dict(recdim=d, layer=K, lr=lr, decay=decay, bpr_batch_size=B, device=dev, test_u_batch_size=128,
+                   dist_exchange=exchange)
         ds = BasicDataset(int(g["n_users"]), int(g["m_items"]), g["train_user"], g["train_item"], g["test_user"],
                           g["test_item"], config=cfg, device=dev)
         E0 = torch.from_numpy(g["E0"]).to(dev)
@@ -56,7 +57,7 @@ def _worker(rank, world, port, ret):
         sm.eval()
         sidx, sval = sm.getUsersTopK(mine, 20, precision="fp32")
         same = float((sidx == idx).float().mean())
-        ret[rank] = (e_prop, l1, l2, e_emb, same, float(g["step1_loss"]), float(g["step2_loss"]))
+        ret[rank] = (e_prop, l1, l2, e_emb, same, float(g["step1_loss"]), float(g["step2_loss"]), dm.exchange)
     finally:
         dist.destroy_process_group()
 
@@ -69,13 +70,17 @@ def _gather(dm, local):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_row_partitioned_training_matches_reference_2gpu():
+@pytest.mark.parametrize("exchange", ["nccl", "push"])
+@pytest.mark.timeout(120)
+def test_row_partitioned_training_matches_reference_2gpu(exchange):
+    """nccl: ncclAllGather per layer; push: all-gather fused into the SpMM epilogue (NVLink peer stores)."""
     world, port = 2, _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, ret, exchange), nprocs=world, join=True)
         for rank in range(world):
-            e_prop, l1, l2, e_emb, same, g1, g2 = ret[rank]
+            e_prop, l1, l2, e_emb, same, g1, g2, used = ret[rank]
+            assert used == exchange
             assert e_prop < 1e-5, e_prop
             assert abs(l1 - g1) < 1e-5 * g1 and abs(l2 - g2) < 1e-5 * g2, (l1, g1, l2, g2)
             assert e_emb < 1e-6, e_emb
