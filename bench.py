@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "push", "nccl"],
+                    help="N>1: push = all-gather fused into the SpMM epilogue over NVLink peer memory")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "hbm"],
                     help="hbm: 2.4M x 0.6M x 60M-edge graph, d=128 (table >> L2) for the honest HBM roofline")
     return ap.parse_args()
@@ -180,7 +182,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if args.workload == "hbm":
         W.update(n_users=2_400_000, m_items=600_000, n_interactions=75_000_000, d=128)
     cfg = dict(recdim=W["d"], layer=W["layers"], lr=W["lr"], decay=W["decay"],
-               bpr_batch_size=W["batch"], device=dev, test_u_batch_size=10000, storage_dtype=args.storage)
+               bpr_batch_size=W["batch"], device=dev, test_u_batch_size=10000, storage_dtype=args.storage,
+               dist_exchange=args.exchange)
     if args.workload == "hbm":
         from furusato_recommend_b200.dataloader import DeviceDataset
         n, m, tu, ti, su, si = bipartite(W["n_users"], W["m_items"], W["n_interactions"], seed=W["seed"], device=dev)
@@ -386,7 +389,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                    f"five-core bipartite graph {n} users x {m} items, nnz(A_hat)={nnz}",
                        "l2": "256 MiB buffer written between timed steps (L2 flush, untimed)",
                        "parallelism": "1 GPU" if world == 1 else
-                       f"{world} GPUs: rows partitioned by nnz, per-layer NCCL all-gather (2K per step) + one 3B-row all-reduce"},
+                       f"{world} GPUs: rows partitioned by nnz; per-layer exchange = " +
+                       ("all-gather fused into the SpMM epilogue (NVLink peer stores, symmetric memory)"
+                        if getattr(model, "exchange", "") == "push" else "ncclAllGather") +
+                       " (2K per step) + one 3B-row all-reduce"},
             "e2e": {"value": nnz_total * K / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 3 * B * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps * 1e3},
             "gpu_launches": launches_per_step * args.steps,
