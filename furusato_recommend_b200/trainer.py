@@ -72,6 +72,13 @@ class Trainer:
             out.append(idx_all[s0:s0 + int(self.config["test_u_batch_size"])].to(torch.int64).cpu())
         return out
 
+    def export_candidates(self, path: str, k: int = 50) -> torch.Tensor:
+        """eval.py:35-40: the re-ranker's input file — `torch.save` of one int64 [U, k] tensor
+        (train_lgbm.py:113-114 flattens it and assumes k == 50 per user)."""
+        cand = torch.cat(self.get_topk_list(k=k), dim=0)
+        torch.save(cand, path)
+        return cand
+
     @torch.no_grad()
     def test(self) -> Dict[str, np.ndarray]:
         """trainer.py:115-187 (hot-path metrics only): recall / precision / ndcg / hr @ topks."""

@@ -373,6 +373,15 @@ def test_get_topk_list_format(golden):
         float((lists[0][:, :20] == torch.from_numpy(golden["topk_raw_idx"])[: len(lists[0])]).float().mean()) > 0.98
 
 
+def test_export_candidates_file_format(golden, tmp_path):
+    model = golden_model(golden, weights="E2")
+    tr = Trainer(model.config, model.dataset, model)
+    cand = tr.export_candidates(str(tmp_path / "lightgcn_result.pt"), k=50)   # eval.py:35-40
+    back = torch.load(tmp_path / "lightgcn_result.pt")
+    assert back.dtype == torch.int64 and back.shape == (len(golden["eval_users"]), 50) and torch.equal(back, cand)
+    assert len(back.flatten()) // 50 == len(golden["eval_users"])                # train_lgbm.py:113-114
+
+
 def test_training_reduces_loss_and_improves_recall():
     n, m, tu, ti, su, si = bipartite(3000, 2000, 80000, seed=3)
     cfg = dict(recdim=64, layer=3, lr=1e-2, decay=1e-4, bpr_batch_size=2048, device=DEV, test_u_batch_size=1000)
