@@ -39,7 +39,7 @@ __device__ __forceinline__ bool contains_sorted(const int32_t* __restrict__ a, i
 __global__ void __launch_bounds__(256)
 uniform_sample_kernel(const int64_t* __restrict__ pos_rowptr, const int32_t* __restrict__ pos_file,
                       const int32_t* __restrict__ pos_sorted, uint32_t n_users, uint32_t m_items,
-                      int64_t first, int64_t count, uint32_t seed_lo, uint32_t seed_hi,
+                      int64_t first, int64_t count, int n_neg, uint32_t seed_lo, uint32_t seed_hi,
                       uint32_t epoch, int64_t* __restrict__ triples, uint8_t* __restrict__ valid) {
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= count) return;
@@ -49,27 +49,32 @@ uniform_sample_kernel(const int64_t* __restrict__ pos_rowptr, const int32_t* __r
   const int64_t user = __umulhi(r[0], n_users);
   const int64_t b = pos_rowptr[user], e = pos_rowptr[user + 1];
   const int64_t len = e - b;
-  int64_t* o = triples + 3 * slot;
+  int64_t* o = triples + 3 * slot * n_neg;
+  uint8_t* vo = valid + slot * n_neg;
   if (len == 0) {
-    valid[slot] = 0;
-    o[0] = user; o[1] = -1; o[2] = -1;
+    for (int t = 0; t < n_neg; ++t) {
+      vo[t] = 0;
+      o[3 * t] = user; o[3 * t + 1] = -1; o[3 * t + 2] = -1;
+    }
     return;
   }
   const int64_t positem = pos_file[b + __umulhi(r[1], (uint32_t)len)];
-  int32_t negitem;
   uint32_t j = 2, blk = 0;
-  for (;;) {
-    if ((j >> 2) != blk) {
-      blk = j >> 2;
-      r[0] = (uint32_t)(i & 0xffffffffu); r[1] = (uint32_t)((uint64_t)i >> 32); r[2] = blk; r[3] = epoch;
-      philox4x32_10(r, seed_lo, seed_hi);
+  for (int t = 0; t < n_neg; ++t) {   // n_neg > 1: the sampled-softmax layout, flat (u, pos, neg_t) rows
+    int32_t negitem;
+    for (;;) {
+      if ((j >> 2) != blk) {
+        blk = j >> 2;
+        r[0] = (uint32_t)(i & 0xffffffffu); r[1] = (uint32_t)((uint64_t)i >> 32); r[2] = blk; r[3] = epoch;
+        philox4x32_10(r, seed_lo, seed_hi);
+      }
+      negitem = (int32_t)__umulhi(r[j & 3u], m_items);
+      ++j;
+      if (!contains_sorted(pos_sorted + b, len, negitem)) break;
     }
-    negitem = (int32_t)__umulhi(r[j & 3u], m_items);
-    ++j;
-    if (!contains_sorted(pos_sorted + b, len, negitem)) break;
+    vo[t] = 1;
+    o[3 * t] = user; o[3 * t + 1] = positem; o[3 * t + 2] = negitem;
   }
-  valid[slot] = 1;
-  o[0] = user; o[1] = positem; o[2] = negitem;
 }
 
 // ---- order-preserving compaction: count per 1024-tile, scan tiles, scatter ----
@@ -168,17 +173,19 @@ using namespace lgcn;
 
 extern "C" int lgcn_uniform_sample(const int64_t* pos_rowptr, const int32_t* pos_file,
                                    const int32_t* pos_sorted, int64_t n_users, int64_t m_items,
-                                   int64_t first, int64_t count, uint64_t seed, uint32_t epoch,
-                                   int64_t* triples, uint8_t* valid, lgcn_stream_t stream) {
+                                   int64_t first, int64_t count, int n_neg, uint64_t seed,
+                                   uint32_t epoch, int64_t* triples, uint8_t* valid,
+                                   lgcn_stream_t stream) {
   LGCN_CHECK_ARG(pos_rowptr && pos_file && pos_sorted && triples && valid, "null pointer argument");
   LGCN_CHECK_ARG(n_users > 0 && n_users < 0xffffffffLL, "n_users out of range");
   LGCN_CHECK_ARG(m_items > 0 && m_items < 0x7fffffffLL, "m_items out of range");
   LGCN_CHECK_ARG(count >= 0 && first >= 0, "negative count/first");
+  LGCN_CHECK_ARG(n_neg >= 1 && n_neg <= 4096, "n_neg must be in [1, 4096]");
   if (count == 0) return 0;
   const int64_t blocks = (count + 255) / 256;
   LGCN_CHECK_ARG(blocks < 0x7fffffffLL, "count too large");
   uniform_sample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      pos_rowptr, pos_file, pos_sorted, (uint32_t)n_users, (uint32_t)m_items, first, count,
+      pos_rowptr, pos_file, pos_sorted, (uint32_t)n_users, (uint32_t)m_items, first, count, n_neg,
       (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), epoch, triples, valid);
   LGCN_LAUNCH_OK();
   return 0;

@@ -25,7 +25,9 @@ def UniformSample(dataset, neg_ratio: int = 1, *, seed: int | None = None, epoch
                   count: int | None = None, start: int = 0) -> torch.Tensor:
     """Returns S: int64 CUDA tensor [n_s, 3] = (user, positem, negitem), n_s <= trainDataSize.
 
-    `neg_ratio` is accepted and ignored, exactly like the reference (:98).  Each call
+    `neg_ratio` = negatives per (user, positive).  The reference accepts and ignores it (:98), i.e.
+    always 1; values > 1 produce the flat-triple layout the sampled-softmax variant batches
+    (model/lgcnssm.py:141): neg_ratio consecutive rows (u, pos, neg_t) per sample.  Each call
     without an explicit `epoch` advances the module's epoch counter, which plays the
     role of the reference's advancing global RNG state.  `start`/`count` select the
     sub-range of sample indices [start, start+count) (multi-GPU sharding)."""
@@ -38,5 +40,5 @@ def UniformSample(dataset, neg_ratio: int = 1, *, seed: int | None = None, epoch
         count = dataset.trainDataSize  # negative_sample.py:106
     rowptr, file_items, sorted_items = dataset.pos_csr()
     triples, valid = ops.uniform_sample(rowptr, file_items, sorted_items, dataset.n_users, dataset.m_items,
-                                        count, seed, epoch, first=start)
+                                        count, seed, epoch, first=start, n_neg=max(1, int(neg_ratio)))
     return ops.compact_triples(triples, valid)

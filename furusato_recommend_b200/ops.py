@@ -131,15 +131,16 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch
 
 
 def uniform_sample(pos_rowptr: torch.Tensor, pos_file: torch.Tensor, pos_sorted: torch.Tensor,
-                   n_users: int, m_items: int, count: int, seed: int, epoch: int, first: int = 0):
+                   n_users: int, m_items: int, count: int, seed: int, epoch: int, first: int = 0,
+                   n_neg: int = 1):
     """Returns (triples int64[count,3], valid uint8[count]) — not yet compacted."""
     lib = _lib.load()
     dev = pos_rowptr.device
-    triples = torch.empty((count, 3), dtype=torch.int64, device=dev)
-    valid = torch.empty(count, dtype=torch.uint8, device=dev)
+    triples = torch.empty((count * n_neg, 3), dtype=torch.int64, device=dev)
+    valid = torch.empty(count * n_neg, dtype=torch.uint8, device=dev)
     _lib.check(lib.lgcn_uniform_sample(
         _chk(pos_rowptr, torch.int64, "pos_rowptr"), _chk(pos_file, torch.int32, "pos_file"),
-        _chk(pos_sorted, torch.int32, "pos_sorted"), n_users, m_items, first, count,
+        _chk(pos_sorted, torch.int32, "pos_sorted"), n_users, m_items, first, count, n_neg,
         seed & 0xFFFFFFFFFFFFFFFF, epoch & 0xFFFFFFFF, triples.data_ptr(), valid.data_ptr(), _stream()),
         "lgcn_uniform_sample")
     return triples, valid

@@ -171,12 +171,14 @@ int lgcn_adam_step(float* param, const float* grad, float* m, float* v, int64_t 
  * (:119-120), draws 2.. the first item not contained in the user's positives
  * (:121-126, membership by binary search in the sorted copy).  Users with an
  * empty list get valid[i]=0 (:116-117).  Samples [first, first+count) are drawn
- * (a shard is a counter offset); triples: int64[count,3].
+ * (a shard is a counter offset).  n_neg > 1 draws n_neg negatives per (user, positive) from the
+ * following Philox words and emits n_neg flat rows (u, pos, neg_t) per sample — the batch layout
+ * of model/lgcnssm.py:141.  triples: int64[count*n_neg, 3], valid: uint8[count*n_neg].
  * ------------------------------------------------------------------------ */
 int lgcn_uniform_sample(const int64_t* pos_rowptr, const int32_t* pos_file, const int32_t* pos_sorted,
                         int64_t n_users, int64_t m_items, int64_t first, int64_t count,
-                        uint64_t seed, uint32_t epoch, int64_t* triples, uint8_t* valid,
-                        lgcn_stream_t stream);
+                        int n_neg, uint64_t seed, uint32_t epoch, int64_t* triples,
+                        uint8_t* valid, lgcn_stream_t stream);
 
 /* Order-preserving compaction of the valid triples (np.array(S), :134).
  * scratch: int64[ceil(count/1024) + 1]; n_out: device int64[1]. */

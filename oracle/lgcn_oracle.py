@@ -214,7 +214,7 @@ def sparse_graph_full(graph):
 # 9.4 sampler  (negative_sample.py:98-134)
 # --------------------------------------------------------------------------
 def uniform_sample_core(all_pos: Sequence[np.ndarray], sample_users: np.ndarray,
-                        next_int: Callable[[int, int], int]) -> np.ndarray:
+                        next_int: Callable[[int, int], int], n_neg: int = 1) -> np.ndarray:
     """The reference's per-sample decision procedure, RNG factored out.
 
     negative_sample.py:113-130: for each drawn user IN ORDER: empty positive
@@ -229,12 +229,13 @@ def uniform_sample_core(all_pos: Sequence[np.ndarray], sample_users: np.ndarray,
         if len(P) == 0:
             continue
         positem = P[next_int(i, len(P))]
-        while True:
-            neg = next_int(i, -1)
-            if neg in P:
-                continue
-            break
-        S.append([int(user), int(positem), int(neg)])
+        for _ in range(n_neg):  # n_neg > 1: flat (u, pos, neg_t) rows, the lgcnssm.py:141 batch layout
+            while True:
+                neg = next_int(i, -1)
+                if neg in P:
+                    continue
+                break
+            S.append([int(user), int(positem), int(neg)])
     return np.array(S, dtype=np.int64).reshape(-1, 3)
 
 
@@ -287,7 +288,7 @@ def philox_randint(r: int, k: int) -> int:
 
 
 def uniform_sample_philox(all_pos: Sequence[np.ndarray], n_users: int, m_items: int,
-                          count: int, seed: int, epoch: int) -> Tuple[np.ndarray, np.ndarray]:
+                          count: int, seed: int, epoch: int, n_neg: int = 1) -> Tuple[np.ndarray, np.ndarray]:
     """Sampler with the "same uniform draws" contract of SURVEY §9.4.
 
     Draw j of sample i is word (j % 4) of Philox4x32-10(key=(seed_lo, seed_hi),
@@ -323,7 +324,7 @@ def uniform_sample_philox(all_pos: Sequence[np.ndarray], n_users: int, m_items: 
         return philox_randint(draw(i), m_items if k < 0 else k)
 
     valid = np.array([len(all_pos[int(u)]) > 0 for u in sample_users], dtype=bool)
-    S = uniform_sample_core(all_pos, sample_users, next_int)
+    S = uniform_sample_core(all_pos, sample_users, next_int, n_neg)
     return S, valid
 
 

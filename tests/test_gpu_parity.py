@@ -259,6 +259,46 @@ def test_sampler_bit_exact(golden, tiny_lists):
     assert len(a) == ds.trainDataSize and not torch.equal(a, b)
 
 
+def test_sampler_multi_negative_and_ssm_variant(golden, tiny_lists):
+    """cfg-4 shape on the tiny graph: J negatives per positive as flat triples, and the
+    reference's lgcnssm arithmetic (BPR softplus over J*B rows per step, lgcnssm.py:98-153)."""
+    from furusato_recommend_b200 import LightGCNSSM
+    train, _ = tiny_lists
+    ds = golden_dataset(golden)
+    J = 8
+    S = UniformSample(ds, neg_ratio=J, seed=7, epoch=1, count=300)
+    want, _ = orc.uniform_sample_philox(train, ds.n_users, ds.m_items, 300, seed=7, epoch=1, n_neg=J)
+    assert np.array_equal(S.cpu().numpy(), want)
+    d, K, B = (int(x) for x in golden["config"])
+    lr, decay = (float(x) for x in golden["hyper"])
+    cfg = dict(recdim=d, layer=K, lr=lr, decay=decay, bpr_batch_size=B, device=DEV, neg_size=J)
+    model = LightGCNSSM(cfg, ds)
+    with torch.no_grad():
+        model.all_embedding.weight.copy_(torch.from_numpy(golden["E0"]))
+    model.train()
+    u, p, q = (S[:, j].contiguous() for j in range(3))
+    loss = model.OneEpoch(u, p, q)
+    om = orc.OracleModel(ds.n_users, ds.m_items, golden["train_user"], golden["train_item"],
+                         torch.from_numpy(golden["E0"]), K, lr, decay)
+    tot = 0.0
+    for i in range(0, len(u), J * B):   # lgcnssm.py:141: batch_size = neg_size * bpr_batch_size
+        tot += float(om.stage_one(u[i:i + J * B].cpu(), p[i:i + J * B].cpu(), q[i:i + J * B].cpu()))
+    want_loss = tot / (len(u) // B + 1)
+    assert abs(float(loss) - want_loss) <= RTOL * abs(want_loss)
+    assert_close(model.all_embedding.weight, om.weight.detach(), what="E after the SSM-variant epoch")
+    l0, r0 = model.softmax_loss(u[:J * B], p[:J * B], q[:J * B])
+    l1, r1 = model.bpr_loss(u[:J * B], p[:J * B], q[:J * B])
+    assert float(l0) == float(l1) and float(r0) == float(r1)   # byte-for-byte the BPR loss, as in the reference
+    # opt-in real sampled softmax (own spec, SURVEY 9.7): finite, decreases under its own steps
+    cfg2 = dict(cfg, ssm_true_softmax=True, lr=1e-2)
+    m2 = LightGCNSSM(cfg2, ds)
+    m2.train()
+    first = float(m2.stageOne(u[:J * B], p[:J * B], q[:J * B]))
+    for _ in range(5):
+        last = float(m2.stageOne(u[:J * B], p[:J * B], q[:J * B]))
+    assert np.isfinite(first) and last < first
+
+
 def test_sampler_skips_users_without_positives():
     # users 1 and 3 have no train line: their samples vanish and order is preserved
     tu, ti = np.array([0, 0, 2, 4, 4, 4]), np.array([1, 2, 0, 3, 1, 0])

@@ -118,3 +118,15 @@ def test_masked_topk_tie_rule_and_mask_reentry():
     vals, idx = orc.masked_topk(r, [np.array([], dtype=np.int64), np.array([2])], 3)
     assert idx[0].tolist() == [1, 2, 4]
     assert idx[1].tolist() == [2, 3, 0] and vals[1].tolist() == [-1024.0, -1500.0, -2000.0]
+
+
+def test_philox_sampler_multi_negative_layout(tiny_lists, golden):
+    """n_neg > 1: n_neg consecutive flat (u, pos, neg_t) rows per sample (lgcnssm.py:141 batches);
+    sample i keeps the same user / positive as with n_neg == 1 and its first negative."""
+    train, _ = tiny_lists
+    n, m = int(golden["n_users"]), int(golden["m_items"])
+    S1, _ = orc.uniform_sample_philox(train, n, m, 50, seed=7, epoch=1)
+    S4, _ = orc.uniform_sample_philox(train, n, m, 50, seed=7, epoch=1, n_neg=4)
+    assert S4.shape == (200, 3) and np.array_equal(S4[::4], S1)
+    for u, p, q in S4:
+        assert p in train[u] and q not in train[u]
