@@ -82,8 +82,8 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
             a.dst_peers[i] = ptr
     for t, nm in ((None if dst_peers else dst, "dst"), (base, "base"), (acc_in, "acc_in"), (acc_out, "acc_out"), (emb, "emb"),
                   (grad, "grad"), (adam_m, "adam_m"), (adam_v, "adam_v")):
-        if t is not None and tuple(t.shape) != (N, d):
-            raise ValueError(f"{nm} must be [{N}, {d}], got {tuple(t.shape)}")
+        if t is not None and (t.dim() != 2 or t.shape[0] < N or t.shape[1] != d):
+            raise ValueError(f"{nm} must be [>={N}, {d}], got {tuple(t.shape)}")
     _lib.check(lib.lgcn_propagate_layer(C.byref(g.c_struct(d)), C.byref(a), _stream()), "lgcn_propagate_layer")
 
 

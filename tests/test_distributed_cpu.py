@@ -23,9 +23,10 @@ def _free_port():
 
 
 def _cpu_local_spmm(rp, col, dinv):
-    """lgcn_propagate_layer's contract (scale_src=0) in plain torch, for the rank's local CSR."""
-    R = rp.numel() - 1
-    rows = torch.repeat_interleave(torch.arange(R), rp[1:] - rp[:-1])
+    """lgcn_propagate_layer's contract (scale_src=0) in plain torch, for the rank's local CSR
+    (CSR rows = the rank's real rows; buffers are padded to R = len(dinv))."""
+    n_real, R = rp.numel() - 1, dinv.numel()
+    rows = torch.repeat_interleave(torch.arange(n_real), rp[1:] - rp[:-1])
 
     def f(src_full, dst=None, base=None, acc_in=None, acc_out=None, acc_scale=1.0, **kw):
         s = torch.zeros((R, src_full.shape[1])).index_add_(0, rows, src_full[col.long()].float())
@@ -48,7 +49,7 @@ def _worker(rank, world, port, ret):
         n, m = int(g["n_users"]), int(g["m_items"])
         K = int(g["config"][1])
         csr = G.build_csr_graph(n, m, torch.from_numpy(g["train_user"]), torch.from_numpy(g["train_item"]))
-        part = RowPartition(csr.rowptr, world)
+        part = RowPartition(csr.rowptr, world, n_users=n if os.environ.get("LGCN_TEST_TWO_SIDED", "1") == "1" else None)
         rp, colp, dl = part.local_csr(rank, csr.rowptr, csr.col, csr.dinv)
         prop = DistPropagator(part, rank, dl, K, _cpu_local_spmm(rp, colp, dl))
         E = torch.from_numpy(g["E0"])
@@ -79,34 +80,40 @@ def _worker(rank, world, port, ret):
         ids = part.to_padded(torch.tensor([0, n + 3, 5, n + m - 1, 5, 299, n]))
         rows, mine = exchange_rows(part, rank, emb, ids)
         err_x = float((rows - E[torch.tensor([0, n + 3, 5, n + m - 1, 5, 299, n])]).abs().max())
-        ret[rank] = (err_f, err_b, err_x, int(mine.sum()), part.R, part.starts.tolist())
+        ret[rank] = (err_f, err_b, err_x, int(mine.sum()), part.R, [c.tolist() for c in part.cuts])
     finally:
         dist.destroy_process_group()
 
 
-def test_row_partition_indexing():
+@pytest.mark.parametrize("n_users", [None, 3])
+def test_row_partition_indexing(n_users):
     rowptr = torch.tensor([0, 4, 4, 10, 11, 11, 30, 31, 40])
     for world in (1, 2, 3, 4):
-        p = RowPartition(rowptr, world)
-        assert p.starts[0] == 0 and p.starts[-1] == 8 and bool((p.starts[1:] >= p.starts[:-1]).all())
+        p = RowPartition(rowptr, world, n_users=n_users)
+        assert sum(p.rows) == 8 and p.R == max(p.rows)
         ids = torch.arange(8)
         pad = p.to_padded(ids)
         assert len(torch.unique(pad)) == 8 and int(pad.max()) < world * p.R
         own = p.owner(ids)
+        assert torch.equal(own, pad // p.R)
         for r in range(world):
-            lo, hi = p.block(r)
-            assert bool((own[lo:hi] == r).all())
+            for lo, hi in p.ranges(r):
+                assert bool((own[lo:hi] == r).all())
         x = torch.arange(16.0).reshape(8, 2)
         gathered = torch.cat([p.shard(r, x) for r in range(world)])
         assert torch.equal(p.unshard(gathered), x)
+        assert torch.equal(gathered[pad], x)          # padded id addresses the gathered layout
         # every edge lands in exactly one local CSR with a remapped column
         col = torch.arange(40, dtype=torch.int32) % 8
         tot = 0
         for r in range(world):
             rp, colp, dl = p.local_csr(r, rowptr, col, torch.ones(8))
-            assert rp.numel() == p.R + 1 and int(rp[-1]) == colp.numel()
+            assert rp.numel() == p.rows[r] + 1 and int(rp[-1]) == colp.numel() and dl.numel() == p.R
             tot += colp.numel()
         assert tot == 40
+    if n_users is not None:  # two-sided: both sides are cut separately, rows stay balanced
+        p = RowPartition(rowptr, 2, n_users=n_users)
+        assert len(p.cuts) == 2 and p.cuts[0][0] == 0 and p.cuts[0][-1] == 3 and p.cuts[1][0] == 3 and p.cuts[1][-1] == 8
 
 
 @pytest.mark.timeout(300)
