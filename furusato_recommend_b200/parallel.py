@@ -247,7 +247,8 @@ def exchange_rows(part: RowPartition, rank: int, local: torch.Tensor, padded_ids
     """rows[i] = TABLE[padded_ids[i]] where TABLE is row-partitioned: owners fill, one all-reduce.
     Sync-free (no boolean indexing): non-owners gather a valid dummy row and multiply it by 0."""
     mine = (padded_ids // part.R) == rank
-    buf = local[padded_ids % part.R] * mine[:, None].to(local.dtype)
+    # where(), not a 0/1 multiply: a non-owner's dummy row may be uninitialised padding (NaN * 0 = NaN)
+    buf = torch.where(mine[:, None], local[padded_ids % part.R], torch.zeros((), dtype=local.dtype, device=local.device))
     if part.world > 1:
         dist.all_reduce(buf, group=group)
     return buf, mine
@@ -275,7 +276,7 @@ class DistLightGCN:
         self.emb = torch.randn((R, d), generator=gen, device=dev) * 0.1      # model/lgcn.py:75, local rows
         self.emb[self.part.rows[rank]:] = 0
         self.m1, self.v1 = torch.zeros_like(self.emb), torch.zeros_like(self.emb)
-        self.acc, self.out = torch.empty_like(self.emb), torch.empty_like(self.emb)
+        self.acc, self.out = torch.zeros_like(self.emb), torch.zeros_like(self.emb)
         self.G = torch.zeros_like(self.emb)
         self.cnt = torch.zeros(R, dtype=torch.int32, device=dev)
         self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -377,7 +378,7 @@ class DistLightGCN:
         ops.bpr_fwd_bwd(out_c, emb_c, ar, ar, ar + B, B, decay, G_c, cnt_c, self.loss_out, self._work,
                         self.work_counter)
         loc = ids % part.R                      # owners add their rows, everyone else adds zeros to a valid row
-        self.G.index_add_(0, loc, G_c * mine[:, None].to(G_c.dtype))
+        self.G.index_add_(0, loc, torch.where(mine[:, None], G_c, torch.zeros((), dtype=G_c.dtype, device=G_c.device)))
         self.cnt.index_add_(0, loc, cnt_c * mine.to(cnt_c.dtype))
         ops.adam_tick(self.step_t, self.hp, float(self.config["lr"]))
         self.prop.backward(self.G, grad_mode=2, inv_layers=1.0 / (self.K + 1), reg_coef=decay / B, cnt=self.cnt,
