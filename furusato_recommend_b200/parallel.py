@@ -243,12 +243,16 @@ class PushPropagator:
         self._run(G_local, lambda k, last: dict(base=G_local, **(last_kwargs if last else {})))
 
 
-def exchange_rows(part: RowPartition, rank: int, local: torch.Tensor, padded_ids: torch.Tensor, group=None):
+def exchange_rows(part: RowPartition, rank: int, local, padded_ids: torch.Tensor, group=None):
     """rows[i] = TABLE[padded_ids[i]] where TABLE is row-partitioned: owners fill, one all-reduce.
-    Sync-free (no boolean indexing): non-owners gather a valid dummy row and multiply it by 0."""
+    `local` may be a list of tables (their rows are concatenated along dim 1 AFTER the gather, so
+    only 3B rows are ever copied).  Sync-free (no boolean indexing); where(), not a 0/1 multiply:
+    a non-owner's dummy row may be uninitialised padding (NaN * 0 = NaN)."""
+    tables = list(local) if isinstance(local, (list, tuple)) else [local]
     mine = (padded_ids // part.R) == rank
-    # where(), not a 0/1 multiply: a non-owner's dummy row may be uninitialised padding (NaN * 0 = NaN)
-    buf = torch.where(mine[:, None], local[padded_ids % part.R], torch.zeros((), dtype=local.dtype, device=local.device))
+    loc = padded_ids % part.R
+    rows = torch.cat([t[loc] for t in tables], dim=1) if len(tables) > 1 else tables[0][loc]
+    buf = torch.where(mine[:, None], rows, torch.zeros((), dtype=rows.dtype, device=rows.device))
     if part.world > 1:
         dist.all_reduce(buf, group=group)
     return buf, mine
@@ -364,7 +368,7 @@ class DistLightGCN:
         self.prop.forward(self.emb, self.acc, self.out)
         ids = part.to_padded(torch.cat([users, pos + self.n, neg + self.n]))
         # one all-reduce for both the propagated and the ego rows: [3B, 2d]
-        both, mine = exchange_rows(part, self.rank, torch.cat([self.out, self.emb], dim=1), ids, self.group)
+        both, mine = exchange_rows(part, self.rank, [self.out, self.emb], ids, self.group)
         out_c, emb_c = both[:, :self.d].contiguous(), both[:, self.d:].contiguous()
         if self._ar is None or self._ar.numel() != B:
             self._ar = torch.arange(B, device=self.device, dtype=torch.int64)
