@@ -28,6 +28,7 @@
 //                  larger k.  The other accumulator stage is being filled meanwhile.
 // Ties: items arrive in ascending id inside a thread, filters are strict, the
 // final merge orders by (score desc, id asc) => lowest id wins, as in the fp32 path.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -107,6 +108,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+// 64 columns of 16-bit accumulators (one per 32-bit TMEM cell) packed two per register
+__device__ __forceinline__ void tc_ld32_pack16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100 "version 1").
@@ -117,8 +131,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool acc16) {
+  return ((acc16 ? 0u : 1u) << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- packing
@@ -228,6 +243,25 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32], float (&m4)[4]) 
   return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
 }
 
+__device__ __forceinline__ __half2 as_h2(uint32_t x) { return *reinterpret_cast<__half2*>(&x); }
+__device__ __forceinline__ float h2_lo(uint32_t x) { return __half2float(__ushort_as_half((unsigned short)(x & 0xffffu))); }
+__device__ __forceinline__ float h2_hi(uint32_t x) { return __half2float(__ushort_as_half((unsigned short)(x >> 16))); }
+
+// packed-f16 variant: register i holds columns 2i (low) and 2i+1 (high); m4[b] covers registers 8b..8b+7
+__device__ __forceinline__ float max32_h(const uint32_t (&r)[32], float (&m4)[4]) {
+  __half2 m[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m[i] = __hmax2(as_h2(r[2 * i]), as_h2(r[2 * i + 1]));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = __hmax2(m[2 * i], m[2 * i + 1]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 q = __hmax2(m[2 * i], m[2 * i + 1]);
+    m4[i] = fmaxf(__low2float(q), __high2float(q));
+  }
+  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+
 struct Params {
   const uint4* a_packed;   // user tiles, [n_utiles][D/8][128]
   const uint4* b_packed;   // item tiles, [n_itiles][D/8][TN]
@@ -241,16 +275,17 @@ struct Params {
   float* out_val;
   float* dense;            // optional [n_eval, m_items] dump of the accumulators (tests)
   int debug_mode;          // 0 = normal; 1 = epilogue skips the TMEM reads (pipeline experiments)
+  int acc16;               // 1: f16 accumulators, read back two per register (tcgen05.ld pack::16b)
 };
 
-template <int D, int TN, int GROUPS, bool DUMP>
+template <int D, int TN, int GROUPS, bool DUMP, bool ACC16>
 __global__ void __launch_bounds__((kFrontWarps + 4 * GROUPS) * 32, 1)
 score_topk_tc_kernel(const Params p) {
   constexpr int NT = GROUPS * 128;              // epilogue threads
   constexpr uint32_t kABytes = kUM * D * 2;
   constexpr uint32_t kBBytes = TN * D * 2;
   constexpr int kKSteps = D / 16;
-  constexpr uint32_t kIdesc = make_idesc(kUM, TN);
+  constexpr uint32_t kIdesc = make_idesc(kUM, TN, ACC16);
   constexpr int kMaxStages = 8;
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -360,44 +395,57 @@ score_topk_tc_kernel(const Params p) {
     // walk of the user's sorted train positives, in step with the item sweep
     int pp = 0;
     int next_pos = my_npos > 0 ? __ldg(my_pos) : 0x7fffffff;
-    // both epilogue groups work on every tile; group g owns the chunks [g*CPG, (g+1)*CPG)
-    constexpr int CPG = TN / 32 / GROUPS;
+    // both epilogue groups work on every tile; group g owns the chunks [g*CPG, (g+1)*CPG).
+    // A chunk is one tcgen05.ld: 32 fp32 columns, or 64 packed f16 columns (ACC16).
+    constexpr int COLS = ACC16 ? 64 : 32;
+    constexpr int CPG = TN / COLS / GROUPS;
     const int c0 = grp * CPG;
 
     for (int j = 0; j < n_tiles; ++j) {
       const int a = j & 1;
       mbar_wait(bar_tfull + 8 * a, (j >> 1) & 1);
       tc_fence_after();
-      const int item_tile0 = j * TN + c0 * 32;
-      const uint32_t tbase = tmem_base + lane_base + (uint32_t)(a * TN + c0 * 32);
+      const int item_tile0 = j * TN + c0 * COLS;
+      const uint32_t tbase = tmem_base + lane_base + (uint32_t)(a * TN + c0 * COLS);
 #pragma unroll 1
       for (int cc = 0; cc < (p.debug_mode == 1 ? 0 : CPG); ++cc) {
         uint32_t r[32];
         __syncwarp();
-        tc_ld32(tbase + (uint32_t)(cc * 32), r);
+        if (ACC16) tc_ld32_pack16(tbase + (uint32_t)(cc * COLS), r);
+        else tc_ld32(tbase + (uint32_t)(cc * COLS), r);
         tc_wait_ld();
-        const int item0 = item_tile0 + cc * 32;
+        const int item0 = item_tile0 + cc * COLS;
         if (DUMP) {
           if (live) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (item0 + i < p.m_items) p.dense[grow * p.m_items + item0 + i] = __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) {
+              if (ACC16) {
+                if (item0 + 2 * i < p.m_items) p.dense[grow * p.m_items + item0 + 2 * i] = h2_lo(r[i]);
+                if (item0 + 2 * i + 1 < p.m_items) p.dense[grow * p.m_items + item0 + 2 * i + 1] = h2_hi(r[i]);
+              } else {
+                if (item0 + i < p.m_items) p.dense[grow * p.m_items + item0 + i] = __uint_as_float(r[i]);
+              }
+            }
           }
         }
         float m4[4];
-        if (max32(r, m4) > sel.thr) {
+        if ((ACC16 ? max32_h(r, m4) : max32(r, m4)) > sel.thr) {
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             if (m4[b] > sel.thr) {
 #pragma unroll
               for (int i = 8 * b; i < 8 * b + 8; ++i) {
-                const float v = __uint_as_float(r[i]);
-                if (v > sel.thr) {
-                  const SelWalk w = sel_append(sel, pp, next_pos, my_pos, my_npos, v, item0 + i, p.m_items,
-                                               p.mask_value, mv, mi, NT, p.cap, p.k);
-                  sel = w.s;
-                  pp = w.pp;
-                  next_pos = w.next;
+#pragma unroll
+                for (int h = 0; h < (ACC16 ? 2 : 1); ++h) {
+                  const float v = ACC16 ? (h == 0 ? h2_lo(r[i]) : h2_hi(r[i])) : __uint_as_float(r[i]);
+                  if (v > sel.thr) {
+                    const SelWalk w = sel_append(sel, pp, next_pos, my_pos, my_npos, v,
+                                                 ACC16 ? item0 + 2 * i + h : item0 + i, p.m_items,
+                                                 p.mask_value, mv, mi, NT, p.cap, p.k);
+                    sel = w.s;
+                    pp = w.pp;
+                    next_pos = w.next;
+                  }
                 }
               }
             }
@@ -462,15 +510,18 @@ static int launch(const Params& p0, cudaStream_t st) {
   const size_t smem = a_bytes + (size_t)stages * b_bytes + cand + tail;
   const int grid = (p.n_eval + kUM - 1) / kUM;
   const int threads = (kFrontWarps + 4 * GROUPS) * 32;
+#define LGCN_TC_LAUNCH(DUMP_, ACC_)                                                                     \
+  do {                                                                                                    \
+    auto kern = score_topk_tc_kernel<D, TN, GROUPS, DUMP_, ACC_>;                                         \
+    LGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    kern<<<grid, threads, smem, st>>>(p);                                                                 \
+  } while (0)
   if (p.dense != nullptr) {
-    auto kern = score_topk_tc_kernel<D, TN, GROUPS, true>;
-    LGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, threads, smem, st>>>(p);
+    if (p.acc16) LGCN_TC_LAUNCH(true, true); else LGCN_TC_LAUNCH(true, false);
   } else {
-    auto kern = score_topk_tc_kernel<D, TN, GROUPS, false>;
-    LGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, threads, smem, st>>>(p);
+    if (p.acc16) LGCN_TC_LAUNCH(false, true); else LGCN_TC_LAUNCH(false, false);
   }
+#undef LGCN_TC_LAUNCH
   LGCN_LAUNCH_OK();
   return 0;
 }
@@ -479,7 +530,7 @@ template <int D, int TN>
 static int run(const float* user_emb, const float* item_emb, const int64_t* user_ids, int n_eval,
                int m_items, const int64_t* pos_rowptr, const int32_t* pos_sorted, int k,
                float mask_value, int32_t* out_idx, float* out_val, float* dense, void* workspace,
-               size_t workspace_bytes, cudaStream_t st) {
+               size_t workspace_bytes, int acc16, cudaStream_t st) {
   const int64_t n_ut = (n_eval + kUM - 1) / kUM, n_it = ((int64_t)m_items + TN - 1) / TN;
   const size_t a_total = (size_t)n_ut * kUM * D * 2, b_total = (size_t)n_it * TN * D * 2;
   if (workspace == nullptr || workspace_bytes < a_total + b_total) {
@@ -509,6 +560,7 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
   p.n_eval = n_eval; p.m_items = m_items; p.pos_rowptr = pos_rowptr; p.pos_sorted = pos_sorted;
   p.k = k; p.mask_value = mask_value; p.out_idx = out_idx; p.out_val = out_val; p.dense = dense;
   p.stages = 2;
+  p.acc16 = acc16;
   {
     const char* dbg = getenv("LGCN_TC_DEBUG");
     p.debug_mode = dbg ? atoi(dbg) : 0;
@@ -539,12 +591,12 @@ size_t score_topk_tc_workspace(int64_t n_eval, int64_t m_items, int d) {
 int score_topk_tc(const float* user_emb, const float* item_emb, const int64_t* user_ids,
                   int64_t n_eval, int64_t m_items, int d, const int64_t* pos_rowptr,
                   const int32_t* pos_sorted, int k, float mask_value, int32_t* out_idx,
-                  float* out_val, float* dense, void* workspace, size_t workspace_bytes,
+                  float* out_val, float* dense, void* workspace, size_t workspace_bytes, int acc16,
                   cudaStream_t st) {
   switch (d) {
-    case 32: return tc::run<32, 256>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes, st);
-    case 64: return tc::run<64, 256>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes, st);
-    case 128: return tc::run<128, 128>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes, st);
+    case 32: return tc::run<32, 256>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes, acc16, st);
+    case 64: return tc::run<64, 256>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes, acc16, st);
+    case 128: return tc::run<128, 128>(user_emb, item_emb, user_ids, (int)n_eval, (int)m_items, pos_rowptr, pos_sorted, k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes, acc16, st);
     default:
       set_last_error("unsupported embedding width d=%d (supported: 32, 64, 128)", d);
       return LGCN_ERR_UNSUPPORTED;
