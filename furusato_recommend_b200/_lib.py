@@ -13,7 +13,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("LGCN_B200_LIB", PKG / "liblgcn_b200.so"))  # override: tuning variants
 
 ABI_VERSION = 1
-F32, BF16, BF16_F16ACC = 0, 1, 2
+F32, BF16, F16 = 0, 1, 2
 HUB_DEG = 256
 SEG_EDGES = 1024
 MAX_PEERS = 8

@@ -227,11 +227,11 @@ static int score_topk_impl(const float* user_emb, const float* item_emb, const i
   LGCN_CHECK_ARG(m_items > 0 && m_items < 0x7fffffffLL, "m_items out of range");
   LGCN_CHECK_ARG(k >= 1 && k <= 128 && k <= m_items, "k must be in [1, min(128, m_items)]");
   if (n_eval == 0) return 0;
-  if (precision == LGCN_BF16 || precision == LGCN_BF16_F16ACC)
+  if (precision == LGCN_BF16 || precision == LGCN_F16)
     return score_topk_tc(user_emb, item_emb, user_ids, n_eval, m_items, d, pos_rowptr, pos_sorted,
                          k, mask_value, out_idx, out_val, dense, workspace, workspace_bytes,
-                         precision == LGCN_BF16_F16ACC ? 1 : 0, st);
-  LGCN_CHECK_ARG(precision == LGCN_F32, "precision must be LGCN_F32, LGCN_BF16 or LGCN_BF16_F16ACC");
+                         precision == LGCN_F16 ? 1 : 0, st);
+  LGCN_CHECK_ARG(precision == LGCN_F32, "precision must be LGCN_F32, LGCN_BF16 or LGCN_F16");
   if (dense != nullptr) {
     const int rc = lgcn_score_dense_f32(user_emb, item_emb, user_ids, n_eval, m_items, d, dense, st);
     if (rc != 0) return rc;
@@ -248,7 +248,7 @@ static int score_topk_impl(const float* user_emb, const float* item_emb, const i
 
 extern "C" int64_t lgcn_score_topk_workspace_bytes(int64_t n_eval, int64_t m_items, int d,
                                                    int precision) {
-  if ((precision != LGCN_BF16 && precision != LGCN_BF16_F16ACC) || n_eval <= 0 || m_items <= 0) return 0;
+  if ((precision != LGCN_BF16 && precision != LGCN_F16) || n_eval <= 0 || m_items <= 0) return 0;
   return (int64_t)score_topk_tc_workspace(n_eval, m_items, d);
 }
 

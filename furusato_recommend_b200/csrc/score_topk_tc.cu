@@ -132,12 +132,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool acc16) {
-  return ((acc16 ? 0u : 1u) << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
+  // f16 accumulation is only legal with f16 operands (kind::f16: D=f16 requires A=B=f16)
+  return ((acc16 ? 0u : 1u) << 4) | ((acc16 ? 0u : 1u) << 7) | ((acc16 ? 0u : 1u) << 10) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- packing
 // dst tile t: [c = 0..D/8)[r = 0..R) 16-byte vectors = rows t*R+r, elements 8c..8c+7 (bf16)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_bf16_kernel(const float* __restrict__ src, const int64_t* __restrict__ ids, int64_t n_rows, int D,
                  int R, int64_t n_tiles, uint4* __restrict__ dst) {
@@ -152,8 +159,13 @@ pack_bf16_kernel(const float* __restrict__ src, const int64_t* __restrict__ ids,
       const int64_t srow = ids ? ids[row] : row;
       const float4 a = ld_f4(src + srow * D + 8 * c);
       const float4 b = ld_f4(src + srow * D + 8 * c + 4);
-      o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
-      o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+      if (F16) {
+        o.x = pack_f16x2(a.x, a.y); o.y = pack_f16x2(a.z, a.w);
+        o.z = pack_f16x2(b.x, b.y); o.w = pack_f16x2(b.z, b.w);
+      } else {
+        o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+        o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+      }
     }
     const int64_t t = row / R;
     const int r = (int)(row % R);
@@ -544,15 +556,23 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
   {
     const int64_t tot = n_ut * kUM * (D / 8);
     const int64_t blocks = (tot + 255) / 256;
-    pack_bf16_kernel<<<(unsigned)(blocks < cap_blocks ? blocks : cap_blocks), 256, 0, st>>>(
-        user_emb, user_ids, n_eval, D, kUM, n_ut, a_packed);
+    if (acc16)
+      pack_bf16_kernel<true><<<(unsigned)(blocks < cap_blocks ? blocks : cap_blocks), 256, 0, st>>>(
+          user_emb, user_ids, n_eval, D, kUM, n_ut, a_packed);
+    else
+      pack_bf16_kernel<false><<<(unsigned)(blocks < cap_blocks ? blocks : cap_blocks), 256, 0, st>>>(
+          user_emb, user_ids, n_eval, D, kUM, n_ut, a_packed);
     LGCN_LAUNCH_OK();
   }
   {
     const int64_t tot = n_it * TN * (D / 8);
     const int64_t blocks = (tot + 255) / 256;
-    pack_bf16_kernel<<<(unsigned)(blocks < cap_blocks ? blocks : cap_blocks), 256, 0, st>>>(
-        item_emb, nullptr, m_items, D, TN, n_it, b_packed);
+    if (acc16)
+      pack_bf16_kernel<true><<<(unsigned)(blocks < cap_blocks ? blocks : cap_blocks), 256, 0, st>>>(
+          item_emb, nullptr, m_items, D, TN, n_it, b_packed);
+    else
+      pack_bf16_kernel<false><<<(unsigned)(blocks < cap_blocks ? blocks : cap_blocks), 256, 0, st>>>(
+          item_emb, nullptr, m_items, D, TN, n_it, b_packed);
     LGCN_LAUNCH_OK();
   }
   Params p;

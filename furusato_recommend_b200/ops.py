@@ -183,7 +183,7 @@ def score_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, user_ids: torch.T
     dev = item_emb.device
     idx = torch.empty((U, k), dtype=torch.int32, device=dev)
     val = torch.empty((U, k), dtype=torch.float32, device=dev)
-    prec = {"fp32": _lib.F32, "bf16": _lib.BF16, "bf16_f16acc": _lib.BF16_F16ACC}[precision]
+    prec = {"fp32": _lib.F32, "bf16": _lib.BF16, "f16": _lib.F16}[precision]
     nbytes = int(lib.lgcn_score_topk_workspace_bytes(U, m, d, prec))
     ws = _workspace(dev, nbytes) if nbytes else None
     args = [_chk(user_emb, torch.float32, "user_emb"), _chk(item_emb, torch.float32, "item_emb"),

@@ -34,7 +34,7 @@ extern "C" {
 
 #define LGCN_F32 0
 #define LGCN_BF16 1
-#define LGCN_BF16_F16ACC 2 /* score_topk only: bf16 operands, f16 tensor-core accumulators */
+#define LGCN_F16 2 /* score_topk only: f16 operands AND f16 tensor-core accumulators */
 
 /* rows with more than LGCN_HUB_DEG edges are split into CTA-wide segments of at
  * most LGCN_SEG_EDGES edges (host side builds the lists, see graph.py) */
@@ -194,7 +194,7 @@ int lgcn_compact_triples(const int64_t* triples, const uint8_t* valid, int64_t c
  *   user_emb/item_emb: propagated embeddings (light_out halves), fp32 [*,d]
  *   user_ids: int64[n_eval] rows of user_emb to score
  *   precision: LGCN_F32 exact fp32 FMA scores | LGCN_BF16 tcgen05 tensor cores (fp32
- *   accumulate) | LGCN_BF16_F16ACC tcgen05 with f16 accumulators (half the TMEM read-out)
+ *   accumulate) | LGCN_F16 tcgen05 with f16 operands and f16 accumulators (half the TMEM read-out)
  * out_idx int32[n_eval,k] (sorted by score desc, id asc), out_val fp32[n_eval,k].
  * workspace: lgcn_score_topk_workspace_bytes() bytes of device scratch (may be NULL for F32).
  * ------------------------------------------------------------------------ */
