@@ -435,3 +435,81 @@ def test_training_reduces_loss_and_improves_recall():
     assert losses[-1] < losses[0] and r1 > r0 + 0.02, (losses, r0, r1)
     sd = model.state_dict()
     assert list(sd.keys()) == ["all_embedding.weight"] and sd["all_embedding.weight"].shape == (n + m, 64)
+
+
+# ------------------------------------------------------------------ wider shapes / edge cases
+@pytest.mark.parametrize("d,K", [(64, 2), (128, 3), (32, 4)])
+def test_fused_steps_other_widths_and_depths(d, K):
+    """BPR + Horner backward + fused Adam at every supported width, K in {2,3,4}, a batch that
+    is not a multiple of the group size, duplicate rows, zero-degree negatives."""
+    rng = np.random.default_rng(d + K)
+    n, m = 500, 700
+    tu = np.repeat(np.arange(n), rng.integers(1, 9, n))
+    ti = rng.integers(0, m - 20, len(tu))          # the last 20 items have no train edge
+    ds = BasicDataset(n, m, tu, ti, np.array([0]), np.array([1]), config={}, device=DEV)
+    cfg = dict(recdim=d, layer=K, lr=5e-3, decay=1e-3, bpr_batch_size=333, device=DEV)
+    torch.manual_seed(d)
+    model = LightGCN(cfg, ds)
+    model.train()
+    E0 = model.all_embedding.weight.detach().cpu().clone()
+    om = orc.OracleModel(n, m, tu, ti, E0, K, 5e-3, 1e-3)
+    for step in range(3):
+        u = torch.from_numpy(rng.integers(0, n, 333))
+        p = torch.from_numpy(np.array([ti[np.searchsorted(tu, x)] for x in u.numpy()]))
+        q = torch.from_numpy(rng.integers(m - 40, m, 333))   # half of them isolated items
+        l = model.stageOne(u.to(DEV), p.to(DEV), q.to(DEV))
+        lo = om.stage_one(u, p, q)
+        assert abs(l.item() - lo.item()) <= RTOL * abs(lo.item()), (step, l.item(), lo.item())
+    assert_close(model.all_embedding.weight, om.weight.detach(), what=f"E after 3 steps d={d} K={K}")
+
+
+def test_error_behaviour_no_silent_fallback(golden):
+    from furusato_recommend_b200 import _lib
+    model = golden_model(golden)
+    model.train()
+    u, p, q = batch(golden)
+    with pytest.raises(_lib.LgcnLibraryError):      # empty batch: the C ABI refuses, nothing falls back
+        model._fused_step_eager(u[:0], p[:0], q[:0])
+    with pytest.raises(_lib.LgcnLibraryError):      # k larger than the item count
+        model.getUsersTopK(u[:4], model.num_items + 1)
+    with pytest.raises(NotImplementedError):        # layer=0 is MF, outside the path
+        LightGCN(dict(model.config, layer=0), model.dataset)
+    with pytest.raises(_lib.LgcnLibraryError):      # unsupported width is an error, not a slow path
+        LightGCN(dict(model.config, recdim=48), model.dataset).computer()
+
+
+def test_eval_properties_cfg2_scale():
+    """BASELINE cfg-2 shape: sortedness, train positives never returned, fp32 == stable sort of a
+    sampled row block, tensor-core lists agree with fp32 lists up to bf16 near-ties."""
+    n, m, tu, ti, su, si = bipartite(30000, 41000, 1_250_000, seed=2020)
+    cfg = dict(recdim=64, layer=3, lr=1e-4, decay=1e-7, bpr_batch_size=2048, device=DEV, test_u_batch_size=10000)
+    ds = BasicDataset(n, m, tu.numpy(), ti.numpy(), su.numpy(), si.numpy(), config=cfg, device=DEV)
+    torch.manual_seed(1)
+    model = LightGCN(cfg, ds)
+    model.eval()
+    users = torch.from_numpy(ds.test_users()).to(DEV)
+    idx32, val32 = model.getUsersTopK(users, 20, precision="fp32")
+    idx16, val16 = model.getUsersTopK(users, 20, precision="bf16")
+    for idx, val in ((idx32, val32), (idx16, val16)):
+        assert bool((val[:, :-1] >= val[:, 1:]).all())                      # sorted by score
+        tie = val[:, :-1] == val[:, 1:]
+        assert bool((idx[:, :-1][tie] < idx[:, 1:][tie]).all())             # ties by ascending id
+        assert int(idx.min()) >= 0 and int(idx.max()) < m
+        key = torch.unique(tu.to(DEV) * m + ti.to(DEV))
+        got = users[:, None] * m + idx.long()
+        assert not bool(torch.isin(got, key).any())                          # masked positives never surface
+    i2, v2 = model.getUsersTopK(users, 20, precision="fp32")
+    assert torch.equal(i2, idx32) and torch.equal(v2, val32)                 # idempotent / deterministic
+    rows = users[:512]
+    dense = ops.score_dense_f32(*model.computer(), rows)
+    rp, _, srt = ds.pos_csr()
+    for r in range(0, 512, 64):
+        u = int(rows[r])
+        s = dense[r].clone()
+        s[srt[int(rp[u]):int(rp[u + 1])].long()] = -1024.0
+        want = torch.sort(s, descending=True, stable=True)[1][:20]
+        assert torch.equal(want, idx32[r].long())
+    overlap = (idx16[:, :, None] == idx32[:, None, :]).any(-1).float().mean()
+    assert float(overlap) > 0.97, float(overlap)
+    res = Trainer(cfg, ds, model).test()
+    assert set(res) == {"recall", "precision", "hr", "ndcg"} and all(len(v) == 2 for v in res.values())
