@@ -40,14 +40,20 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build_variant(tag: str, defines: dict) -> Path:
-    """Tuning aid: liblgcn_b200_<tag>.so with -D overrides (select it with LGCN_B200_LIB)."""
+def build_variant(tag: str, defines: dict, sources=("spmm.cu",)) -> Path:
+    """Tuning aid: liblgcn_b200_<tag>.so with -D overrides applied to `sources` (the other objects
+    come from the standard build).  Select it at run time with LGCN_B200_LIB=<path>."""
+    build()
     out = PKG / f"liblgcn_b200_{tag}.so"
     objs = []
     for src in SOURCES:
-        obj = CSRC / f"{src[:-3]}_{tag}.o"
-        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in defines.items()], "-c", str(CSRC / src), "-o", str(obj)]
-        subprocess.run(cmd, check=True)
+        if src in sources:
+            obj = CSRC / f"{src[:-3]}_{tag}.o"
+            cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in defines.items()], "-c", str(CSRC / src),
+                   "-o", str(obj)]
+            subprocess.run(cmd, check=True)
+        else:
+            obj = CSRC / (src[:-3] + ".o")
         objs.append(str(obj))
     subprocess.run([_nvcc(), "-shared", "-o", str(out), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
                     "-Xcompiler", "-fPIC", "-lcudart_static", "-ldl", "-lrt", "-lpthread"], check=True)

@@ -73,6 +73,8 @@ struct GraphDev {
 };
 
 struct EpiDev {
+  const float* src_scale;  // w_j of the gather (first layer) and the pre-scale of dst; dinv unless overridden
+  const float* dst_scale;  // x_i = dst_scale[i] * s_i; dinv unless overridden
   const void* src;
   void* dst;
   const float* base;
@@ -98,15 +100,30 @@ struct EpiDev {
 // Sum of w_j * SRC[col[e]] over e = e0, e0+1, .. inside [e0, e_end) taken in
 // chunks of LPR edges that advance by `stride` edges (stride == LPR: the whole
 // range; stride == kGroups*LPR: this group's share of a hub segment).
+//
+// The kernel issues on ~50 % of the cycles (ncu), so the inner loop is kept to
+// SHFL + IMAD.WIDE + LDG.128 + ISETP + 4 predicated FADD/FFMA per neighbour row:
+//   * ALL 32 lanes call this together and every shuffle uses the full mask; trip counts are
+//     made warp-uniform (max over the warp's groups), so there is no divergence bookkeeping
+//     (MATCH/REDUX/VOTE + BRA.DIV per shuffle with a partial mask);
+//   * loads are never predicated and need no zero-fill select: a slot past the end of the
+//     neighbour list re-reads row 0 of SRC (an L1 hit) and is accumulated with weight 0;
+//   * the row address is one mad.wide on a lane-folded base pointer.
 template <int D, bool SRC_BF16, bool SCALE_SRC>
 __device__ __forceinline__ void gather_sum(const void* __restrict__ src,
                                            const int32_t* __restrict__ col,
                                            const float* __restrict__ dinv, int64_t e0,
-                                           int64_t e_end, int64_t stride, int lig, unsigned gmask,
+                                           int64_t e_end, int64_t stride, int lig,
                                            float (&acc)[RowCfg<D, SRC_BF16>::kEPL]) {
   using C = RowCfg<D, SRC_BF16>;
   constexpr int LPR = C::kLPR, EPL = C::kEPL, U = C::kUnroll;
-  const char* rows = reinterpret_cast<const char*>(src) + lig * 16;
+  constexpr unsigned kFull = 0xffffffffu;
+  const char* base = reinterpret_cast<const char*>(src) + lig * 16;
+
+  const int64_t span = e_end - e0;
+  int n_chunks = span > 0 ? (int)((span + stride - 1) / stride) : 0;
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) n_chunks = max(n_chunks, __shfl_xor_sync(kFull, n_chunks, o));
 
   int nxt_c = 0;
   float nxt_w = 0.f;
@@ -114,44 +131,47 @@ __device__ __forceinline__ void gather_sum(const void* __restrict__ src,
     nxt_c = ldg_stream_i32(col + e0 + lig);
     if (SCALE_SRC) nxt_w = __ldg(dinv + nxt_c);
   }
-  for (int64_t e = e0; e < e_end; e += stride) {
-    const int cnt = (e_end - e) < LPR ? int(e_end - e) : LPR;
+  int64_t e = e0;
+  for (int ch = 0; ch < n_chunks; ++ch, e += stride) {
+    const int64_t left = e_end - e;
+    const int cnt = left <= 0 ? 0 : (left < LPR ? (int)left : LPR);
     const int cur_c = nxt_c;
     const float cur_w = nxt_w;
-    const int64_t en = e + stride;
-    if (en + lig < e_end) {  // prefetch the next chunk of column ids
-      nxt_c = ldg_stream_i32(col + en + lig);
+    nxt_c = 0;
+    nxt_w = 0.f;
+    if (e + stride + lig < e_end) {  // prefetch the next chunk of column ids
+      nxt_c = ldg_stream_i32(col + e + stride + lig);
       if (SCALE_SRC) nxt_w = __ldg(dinv + nxt_c);
     }
-    for (int t = 0; t < cnt; t += U) {
+    int nb = (cnt + U - 1) / U;
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) nb = max(nb, __shfl_xor_sync(kFull, nb, o));
+    for (int bt = 0; bt < nb; ++bt) {
       uint4 v[U];
       float w[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int c = __shfl_sync(gmask, cur_c, t + u, LPR);
-        if (SCALE_SRC) w[u] = __shfl_sync(gmask, cur_w, t + u, LPR);
-        if (t + u < cnt) {
-          v[u] = ldg_row16(rows + (int64_t)c * C::kRowBytes);
-        } else {
-          v[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (SCALE_SRC) w[u] = 0.f;
-        }
+        const int c = __shfl_sync(kFull, cur_c, bt * U + u, LPR);
+        if (SCALE_SRC) w[u] = __shfl_sync(kFull, cur_w, bt * U + u, LPR);
+        const char* rp;
+        asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(rp) : "r"(c), "n"(C::kRowBytes), "l"(base));
+        v[u] = ldg_row16(rp);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
+        // weight 0 retires a padding slot without a predicated accumulator write; a real slot of a
+        // pre-scaled source has weight 1, and fma(1, f, acc) == acc + f exactly
+        const float wu = SCALE_SRC ? w[u] : (bt * U + u < cnt ? 1.f : 0.f);
         if (SRC_BF16) {
           float f[8];
           unpack_bf16x8(v[u], f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j % EPL] += f[j];
+          for (int j = 0; j < 8; ++j) acc[j % EPL] = fmaf(wu, f[j], acc[j % EPL]);
         } else {
           const float f[4] = {__uint_as_float(v[u].x), __uint_as_float(v[u].y),
                               __uint_as_float(v[u].z), __uint_as_float(v[u].w)};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (SCALE_SRC) acc[j] = fmaf(w[u], f[j], acc[j]);
-            else acc[j] += f[j];
-          }
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(wu, f[j], acc[j]);
         }
       }
     }
@@ -163,15 +183,16 @@ __device__ __forceinline__ void gather_sum(const void* __restrict__ src,
 // latency hides behind the neighbour loads instead of extending the per-row dependency chain.
 template <int EPL>
 struct RowPre {
-  float di;
+  float di;      // dst_scale[row]
+  float ds;      // src_scale[row] (== di for the symmetric normalisation)
   float v[EPL];  // base[row] (backward) or acc_in[row] (forward)
 };
 
 template <int D, int EPL>
-__device__ __forceinline__ RowPre<EPL> row_prefetch(const EpiDev& p, const float* __restrict__ dinv,
-                                                    int64_t row, int lig) {
+__device__ __forceinline__ RowPre<EPL> row_prefetch(const EpiDev& p, int64_t row, int lig) {
   RowPre<EPL> r;
-  r.di = __ldg(dinv + row);
+  r.di = __ldg(p.dst_scale + row);
+  r.ds = p.src_scale == p.dst_scale ? r.di : __ldg(p.src_scale + row);
   const float* src = p.base != nullptr ? p.base : p.acc_in;
   const int64_t off = row * D + lig * EPL;
 #pragma unroll
@@ -203,7 +224,7 @@ __device__ __forceinline__ void row_epilogue(const EpiDev& p, const RowPre<EPL>&
   if (p.dst != nullptr) {
     float z[EPL];
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) z[j] = di * t[j];
+    for (int j = 0; j < EPL; ++j) z[j] = pre.ds * t[j];
     // n_peer == 0: plain local store.  n_peer > 0: the all-gather is fused here — the row goes to
     // every rank's gathered buffer over NVLink (peer-mapped pointers), at this rank's row block.
     const int n_dst = p.n_peer > 0 ? p.n_peer : 1;
@@ -301,13 +322,15 @@ spmm_layer_kernel(const GraphDev g, const EpiDev p) {
   if ((int)blockIdx.x >= g.n_seg) {
     // ---------------- light rows: one group per row ----------------
     const int64_t gid = (int64_t)(blockIdx.x - g.n_seg) * NG + grp;
-    if (gid >= g.n_light) return;
-    const int4 dsc = __ldg(g.light_desc + gid);  // {row, degree, first edge lo, hi}: one hop, no rowptr
+    const bool live = gid < g.n_light;  // a dead group still takes part in the warp's shuffles
+    int4 dsc = make_int4(0, 0, 0, 0);
+    if (live) dsc = __ldg(g.light_desc + gid);  // {row, degree, first edge lo, hi}: one hop, no rowptr
     const int64_t row = dsc.x;
     const int64_t b = (int64_t)(((uint64_t)(uint32_t)dsc.w << 32) | (uint32_t)dsc.z);
-    const RowPre<EPL> pre = row_prefetch<D, EPL>(p, g.dinv, row, lig);
-    gather_sum<D, SRC_BF16, SCALE_SRC>(p.src, g.col, g.dinv, b, b + dsc.y, LPR, lig, gmask, acc);
-    row_epilogue<D, EPL, DST_BF16>(p, pre, row, lig, gmask, acc);
+    RowPre<EPL> pre;
+    if (live) pre = row_prefetch<D, EPL>(p, row, lig);
+    gather_sum<D, SRC_BF16, SCALE_SRC>(p.src, g.col, p.src_scale, b, b + dsc.y, LPR, lig, acc);
+    if (live) row_epilogue<D, EPL, DST_BF16>(p, pre, row, lig, gmask, acc);
     return;
   }
 
@@ -318,8 +341,8 @@ spmm_layer_kernel(const GraphDev g, const EpiDev p) {
   const int64_t row = g.seg_row[seg];
   const int64_t b = g.seg_begin[seg];
   const int64_t e = b + g.seg_len[seg];
-  gather_sum<D, SRC_BF16, SCALE_SRC>(p.src, g.col, g.dinv, b + (int64_t)grp * LPR, e,
-                                     (int64_t)NG * LPR, lig, gmask, acc);
+  gather_sum<D, SRC_BF16, SCALE_SRC>(p.src, g.col, p.src_scale, b + (int64_t)grp * LPR, e,
+                                     (int64_t)NG * LPR, lig, acc);
 #pragma unroll
   for (int j = 0; j < EPL; ++j) red[grp][lig * EPL + j] = acc[j];
   __syncthreads();
@@ -356,7 +379,7 @@ spmm_layer_kernel(const GraphDev g, const EpiDev p) {
     float s[EPL];
 #pragma unroll
     for (int j = 0; j < EPL; ++j) s[j] = red[0][lig * EPL + j];
-    const RowPre<EPL> pre = row_prefetch<D, EPL>(p, g.dinv, row, lig);
+    const RowPre<EPL> pre = row_prefetch<D, EPL>(p, row, lig);
     row_epilogue<D, EPL, DST_BF16>(p, pre, row, lig, gmask, s);
   }
 }
@@ -481,6 +504,8 @@ extern "C" int lgcn_propagate_layer(const lgcn_graph_t* gh, const lgcn_layer_arg
   g.partial = gh->partial;
 
   EpiDev p;
+  p.src_scale = a->src_scale != nullptr ? a->src_scale : gh->dinv;
+  p.dst_scale = a->dst_scale != nullptr ? a->dst_scale : gh->dinv;
   p.src = a->src; p.dst = a->dst; p.base = a->base;
   p.acc_in = a->acc_in; p.acc_out = a->acc_out; p.acc_scale = a->acc_scale;
   p.grad_mode = a->grad_mode; p.inv_layers = a->inv_layers; p.reg_coef = a->reg_coef;

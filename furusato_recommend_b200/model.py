@@ -124,9 +124,13 @@ class LightGCN(nn.Module):
         self.device = torch.device(config.get("device", "cuda:0"))
         self.storage_dtype = _STORAGE[config.get("storage_dtype", "fp32")]
         self.eval_precision = config.get("eval_precision", "fp32")
-        self.graph: CsrGraph = dataset.csr_graph()
+        self.graph: CsrGraph = self._build_graph(dataset)
         if self.graph.device != self.device:
             self.graph = self.graph.to(self.device)
+        # (column-side, row-side) normalisation vectors of the propagation operator
+        # diag(row) A diag(col); None = the graph's dinv on both sides (D^-1/2 A D^-1/2)
+        self._col_scale: Optional[torch.Tensor] = None
+        self._row_scale: Optional[torch.Tensor] = None
         self.__init_weight()
         self.optim = FusedAdam(self.parameters(), lr=config["lr"])  # model/lgcn.py:63
         self._bufs = {}
@@ -136,6 +140,17 @@ class LightGCN(nn.Module):
         self.use_cuda_graph = bool(config.get("cuda_graph", True))
         self._graph = None
         self._graph_key = None
+
+    def _build_graph(self, dataset: BasicDataset) -> CsrGraph:
+        return dataset.csr_graph()
+
+    def _scales(self, transpose: bool) -> dict:
+        """Scale vectors of one layer: forward diag(row) A diag(col), backward its transpose."""
+        if self._col_scale is None:
+            return {}
+        if transpose:
+            return dict(src_scale=self._row_scale, dst_scale=self._col_scale)
+        return dict(src_scale=self._col_scale, dst_scale=self._row_scale)
 
     def train(self, mode: bool = True):
         # weights only move in training mode; eval mode may reuse one propagation
@@ -203,7 +218,7 @@ class LightGCN(nn.Module):
                 g, emb if k == 0 else z[(k - 1) & 1], scale_src=(k == 0),
                 dst=None if last else z[k & 1],
                 acc_in=emb if k == 0 else acc, acc_out=out if last else acc,
-                acc_scale=1.0 / (K + 1) if last else 1.0)
+                acc_scale=1.0 / (K + 1) if last else 1.0, **self._scales(False))
 
     def _horner_into(self, G: torch.Tensor, *, grad_mode: int, reg_coef: float, cnt: torch.Tensor,
                      grad: Optional[torch.Tensor] = None, adam: Optional[dict] = None) -> None:
@@ -222,7 +237,7 @@ class LightGCN(nn.Module):
                     kw.update(adam_m=adam["exp_avg"], adam_v=adam["exp_avg_sq"], adam_hp=adam["hp"],
                               betas=adam["betas"], eps=adam["eps"], zero_base=K > 1)
             ops.propagate_layer(g, G if j == 0 else z[(j - 1) & 1], scale_src=(j == 0),
-                                dst=None if last else z[j & 1], base=G, **kw)
+                                dst=None if last else z[j & 1], base=G, **kw, **self._scales(True))
 
     def computer(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """Propagated (users, items) embeddings — model/MF.py:178-210 naming."""

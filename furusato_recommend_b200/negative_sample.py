@@ -42,3 +42,40 @@ def UniformSample(dataset, neg_ratio: int = 1, *, seed: int | None = None, epoch
     triples, valid = ops.uniform_sample(rowptr, file_items, sorted_items, dataset.n_users, dataset.m_items,
                                         count, seed, epoch, first=start, n_neg=max(1, int(neg_ratio)))
     return ops.compact_triples(triples, valid)
+
+
+POSITIVE_NUM_LIMIT = 3000   # ddp_lgcn.py:34
+TRAIN_ITERATIVE = 3         # ddp_lgcn.py:35
+
+
+def UniformSampleCapped(dataset, neg_ratio: int = 1, *, limit: int = POSITIVE_NUM_LIMIT,
+                        iterative: int = TRAIN_ITERATIVE, seed: int | None = None, epoch: int | None = None,
+                        count: int | None = None) -> torch.Tensor:
+    """The DDP script's sampler (ddp_lgcn.py:541-582): `trainDataSize * TRAIN_ITERATIVE` draws, and a
+    sample is dropped when its positive item was already emitted `limit` times this epoch (:569-570).
+
+    The cap is order dependent in the reference (a Python dict counted along the loop).  With
+    per-sample Philox streams a dropped sample never shifts another sample's draws, so the same
+    decision is "rank of sample i among the non-empty samples of lower index with the same
+    positive < limit": one stable device sort by positive item, no sequential pass."""
+    if epoch is None:
+        epoch = _STATE["epoch"]
+        _STATE["epoch"] += 1
+    if seed is None:
+        seed = _STATE["seed"]
+    if count is None:
+        count = dataset.trainDataSize * int(iterative)   # ddp_lgcn.py:549
+    rowptr, file_items, sorted_items = dataset.pos_csr()
+    triples, valid = ops.uniform_sample(rowptr, file_items, sorted_items, dataset.n_users, dataset.m_items,
+                                        count, seed, epoch)
+    m = int(dataset.m_items)
+    key = torch.where(valid.bool(), triples[:, 1], torch.full_like(triples[:, 1], m))  # empties sort last
+    skey, order = torch.sort(key, stable=True)
+    pos_in_sorted = torch.arange(count, device=key.device)
+    run_start = torch.zeros(m + 2, dtype=torch.int64, device=key.device)
+    run_start[1:] = torch.cumsum(torch.bincount(skey, minlength=m + 1), 0)
+    rank = pos_in_sorted - run_start[skey]
+    keep_sorted = (rank < int(limit)) & (skey < m)
+    keep = torch.zeros(count, dtype=torch.uint8, device=key.device)
+    keep[order] = keep_sorted.to(torch.uint8)
+    return ops.compact_triples(triples, keep)

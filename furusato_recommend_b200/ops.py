@@ -49,8 +49,11 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
                     grad: Optional[torch.Tensor] = None, adam_m: Optional[torch.Tensor] = None,
                     adam_v: Optional[torch.Tensor] = None, adam_hp: Optional[torch.Tensor] = None,
                     betas=(0.9, 0.999), eps: float = 1e-8, zero_base: bool = False,
-                    dst_peers: Optional[Sequence[int]] = None, dst_row_offset: int = 0) -> None:
-    """lgcn_propagate_layer: one normalised-adjacency SpMM + fused row epilogue."""
+                    dst_peers: Optional[Sequence[int]] = None, dst_row_offset: int = 0,
+                    src_scale: Optional[torch.Tensor] = None, dst_scale: Optional[torch.Tensor] = None) -> None:
+    """lgcn_propagate_layer: one normalised-adjacency SpMM + fused row epilogue.
+    `src_scale` / `dst_scale` ([N] fp32) replace the graph's dinv on the column / row side
+    (rAdjGCN's asymmetric normalisation); None keeps D^-1/2 A D^-1/2."""
     lib = _lib.load()
     n_src, d = src.shape
     N = g.n_nodes  # rows of this (possibly rank-local) graph; src may hold more rows (all-gathered)
@@ -74,6 +77,11 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
     a.adam_hp = _chk(adam_hp, torch.float32, "adam_hp", True)
     a.beta1, a.beta2, a.eps = betas[0], betas[1], eps
     a.zero_base = int(zero_base)
+    for t, nm in ((src_scale, "src_scale"), (dst_scale, "dst_scale")):
+        if t is not None and (t.dim() != 1 or t.shape[0] < N):
+            raise ValueError(f"{nm} must be [>={N}], got {tuple(t.shape)}")
+    a.src_scale = _chk(src_scale, torch.float32, "src_scale", True)
+    a.dst_scale = _chk(dst_scale, torch.float32, "dst_scale", True)
     if dst_peers:
         if dst is None:
             raise ValueError("dst_peers needs dst (it fixes the dtype and enables the write)")

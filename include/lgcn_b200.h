@@ -123,6 +123,13 @@ typedef struct lgcn_layer_args {
   int n_dst_peers;
   int64_t dst_row_offset;
   void* dst_peers[LGCN_MAX_PEERS];
+  /* Asymmetric normalisation (rAdjGCN, model/radj.py:32-45: edge weight deg_src^-r * deg_dst^-(1-r)).
+   * NULL = the graph's dinv.  With both set the layer computes
+   *   w_j = src_scale[j],  x_i = dst_scale[i] * s_i,  dst[i] = src_scale[i] * t_i,
+   * i.e. diag(dst_scale) A diag(src_scale); the transpose for the backward pass is the same
+   * call with the two vectors swapped (A itself is symmetric). */
+  const float* src_scale; /* [N] fp32 or NULL */
+  const float* dst_scale; /* [N] fp32 or NULL */
 } lgcn_layer_args_t;
 
 int lgcn_propagate_layer(const lgcn_graph_t* g /*HOST*/, const lgcn_layer_args_t* a /*HOST*/,

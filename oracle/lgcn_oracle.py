@@ -407,3 +407,139 @@ def evaluate(model: OracleModel, all_pos, test_dict: Dict[int, List[int]], ks: S
         for m in tot:
             tot[m] += bm[m]
     return {m: v / float(len(users)) for m, v in tot.items()}, tops
+
+
+# --------------------------------------------------------------------------
+# f-4 variants on the same kernels: rAdjGCN, RGCN, PyG-LGConv form,
+# capped sampler.  Pinned by oracle/make_golden_variants.py against the live
+# reference classes (their un-vendored imports torch_geometric / torch_scatter
+# are stubbed with the semantics restated below).
+# --------------------------------------------------------------------------
+def directed_edges(n_users: int, train_user, train_item, extra_user=None, extra_item=None):
+    """train_edge of model/radj.py:21-27 / edge_index of model/rgcn.py:54-85:
+    [users -> items+n | items+n -> users], then the favourite edges the same way."""
+    tu = torch.as_tensor(np.asarray(train_user), dtype=torch.int64)
+    ti = torch.as_tensor(np.asarray(train_item), dtype=torch.int64) + n_users
+    e = torch.cat([torch.stack([tu, ti]), torch.stack([ti, tu])], dim=1)
+    if extra_user is not None:
+        fu = torch.as_tensor(np.asarray(extra_user), dtype=torch.int64)
+        fi = torch.as_tensor(np.asarray(extra_item), dtype=torch.int64) + n_users
+        e = torch.cat([e, torch.stack([fu, fi]), torch.stack([fi, fu])], dim=1)
+    return e
+
+
+def scatter_sum(src: torch.Tensor, index: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """torch_scatter.scatter(src, index, out=out, dim=0) with the default reduce='sum'
+    (un-vendored dependency, unpinned version; call sites model/radj.py:44, model/lgcn.py:41)."""
+    return out.index_add(0, index, src)
+
+
+def radj_conv(x: torch.Tensor, edge: torch.Tensor, n_nodes: int, r: float) -> torch.Tensor:
+    """rAdjConv.forward, model/radj.py:28-45: deg = multiplicity-counting out-degree of
+    train_edge[0] (0 -> 1e-6), div_e = deg[src]^r * deg[dst]^(1-r), out[dst] += x[src] / div_e."""
+    all_div = torch.zeros(n_nodes)
+    value, count = torch.unique(edge[0], return_counts=True)
+    all_div[value] = count.float()
+    all_div[all_div == 0] = 1e-6
+    div = (all_div[edge[0]] ** r) * (all_div[edge[1]] ** (1 - r))
+    msg = x[edge[0]] / div.unsqueeze(1)
+    return scatter_sum(msg, edge[1], torch.zeros_like(x))
+
+
+def radj_forward(all_emb: torch.Tensor, edge: torch.Tensor, n_layers: int, n_users: int, r: float):
+    """rAdjGCN.forward, model/radj.py:84-92."""
+    x = all_emb
+    x_out = x
+    for _ in range(n_layers):
+        x = radj_conv(x, edge, all_emb.shape[0], r)
+        x_out = x_out + x
+    x_out = x_out / (1 + n_layers)
+    return x_out[:n_users], x_out[n_users:]
+
+
+def lgconv_pyg(x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    """PyG `LGConv(normalize=True)` = gcn_norm(add_self_loops=False) + sum aggregation
+    (un-vendored torch_geometric, version unpinned; call sites model/lgcn.py:64-66,82,
+    model/rgcn.py:97,112): deg = scatter_add(1, col); w_e = deg[row]^-1/2 deg[col]^-1/2
+    (inf -> 0); out_i = sum_{e: col_e = i} w_e x[row_e].  SURVEY §8c."""
+    row, col = edge_index[0], edge_index[1]
+    n = x.shape[0]
+    deg = torch.zeros(n, dtype=x.dtype).index_add(0, col, torch.ones(col.numel(), dtype=x.dtype))
+    dis = deg.pow(-0.5)
+    dis[dis == float("inf")] = 0
+    w = dis[row] * dis[col]
+    return torch.zeros_like(x).index_add(0, col, w.unsqueeze(1) * x[row])
+
+
+def lgconv_forward(all_emb: torch.Tensor, edge_index: torch.Tensor, n_layers: int, n_users: int):
+    """LightGCN.forward of model/lgcn.py:78-86 (running sum, then / (1 + K)); the same loop is
+    RGCN.forward (model/rgcn.py:108-116) on the purchase + favourite edge_index."""
+    x = all_emb
+    x_out = x
+    for _ in range(n_layers):
+        x = lgconv_pyg(x, edge_index)
+        x_out = x_out + x
+    x_out = x_out / (1 + n_layers)
+    return x_out[:n_users], x_out[n_users:]
+
+
+def bpr_loss_from(all_users, all_items, all_emb, n_users, users, pos, neg):
+    """bpr_loss body shared by model/lgcn.py:98-118, model/radj.py:105-126, model/rgcn.py:129-150."""
+    users, pos, neg = users.long(), pos.long(), neg.long()
+    u, p, q = all_users[users], all_items[pos], all_items[neg]
+    u0, p0, q0 = all_emb[users], all_emb[pos + n_users], all_emb[neg + n_users]
+    reg = 0.5 * (u0.norm(2).pow(2) + p0.norm(2).pow(2) + q0.norm(2).pow(2)) / float(len(users))
+    loss = torch.mean(torch.nn.functional.softplus(torch.sum(u * q, dim=1) - torch.sum(u * p, dim=1)))
+    return loss, reg
+
+
+def capped_sample_core(all_pos: Sequence[np.ndarray], sample_users: np.ndarray,
+                       next_int: Callable[[int, int], int], limit: int) -> np.ndarray:
+    """The DDP script's sampler, ddp_lgcn.py:541-582: as uniform_sample_core, but a sample whose
+    positive item was already emitted `limit` (POSITIVE_NUM_LIMIT = 3000) times this epoch is
+    dropped BEFORE its negative is drawn (:569-570); order dependent."""
+    S = []
+    oc: Dict[int, int] = {}
+    for i, user in enumerate(sample_users):
+        P = all_pos[int(user)]
+        if len(P) == 0:
+            continue
+        positem = int(P[next_int(i, len(P))])
+        if oc.get(positem, 0) >= limit:
+            continue
+        oc[positem] = oc.get(positem, 0) + 1
+        while True:
+            neg = next_int(i, -1)
+            if neg in P:
+                continue
+            break
+        S.append([int(user), positem, int(neg)])
+    return np.array(S, dtype=np.int64).reshape(-1, 3)
+
+
+def capped_sample_mt(all_pos, m_items: int, count: int, limit: int) -> np.ndarray:
+    """ddp_lgcn.py:549-551 with the reference's RNG: users from randint(0, len(allPos), count),
+    count = trainDataSize * TRAIN_ITERATIVE."""
+    sample_users = np.random.randint(0, len(all_pos), count)
+
+    def next_int(_i, k):
+        return np.random.randint(0, m_items if k < 0 else k)
+
+    return capped_sample_core(all_pos, sample_users, next_int, limit)
+
+
+def capped_sample_philox(all_pos, n_users: int, m_items: int, count: int, seed: int, epoch: int,
+                         limit: int) -> np.ndarray:
+    """Capped sampler on the Philox draw mapping of `uniform_sample_philox` (our spec): every
+    sample owns its counter stream, so dropping a sample never shifts another sample's draws and
+    the cap is "rank of sample i among the earlier non-empty samples with the same positive"."""
+    S, _ = uniform_sample_philox(all_pos, n_users, m_items, count, seed, epoch)
+    keep = np.ones(len(S), dtype=bool)
+    oc: Dict[int, int] = {}
+    for t, p in enumerate(S[:, 1].tolist()):
+        c = oc.get(p, 0)
+        if c >= limit:
+            keep[t] = False
+        else:
+            oc[p] = c + 1
+    return S[keep]

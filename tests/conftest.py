@@ -22,6 +22,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def variants():
+    """Golden vectors of the f-4 variants (oracle/make_golden_variants.py, live reference classes)."""
+    return dict(np.load(REPO / "tests" / "golden" / "variants_ref.npz", allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
 def tiny_lists(golden):
     """(train lists in file order, test dict) rebuilt from the golden edge arrays."""
     n = int(golden["n_users"])
