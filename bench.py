@@ -46,9 +46,12 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "push", "nccl"],
                     help="N>1: push = all-gather fused into the SpMM epilogue over NVLink peer memory")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "hbm", "cfg3"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "hbm", "cfg3", "cfg4", "cfg5"],
                     help="hbm: 2.4M x 0.6M x 60M-edge graph, d=128 (table >> L2) for the honest HBM roofline; "
-                         "cfg3: BASELINE configs[2], 10M x 2M x 500M edges, d=128 (graph built on device)")
+                         "cfg3: BASELINE configs[2], 10M x 2M x 500M edges, d=128 (graph built on device); "
+                         "cfg4: configs[3], LightGCNSSM 4-layer d=64, 256 negatives per positive on the same graph; "
+                         "cfg5: configs[4], full-rank top-20 eval of --eval-users users x 2M items, user-sharded")
+    ap.add_argument("--eval-users", type=int, default=1_000_000, help="cfg5: users scored (all ranks together)")
     return ap.parse_args()
 
 
@@ -184,10 +187,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         W.update(n_users=2_400_000, m_items=600_000, n_interactions=75_000_000, d=128)
     if args.workload == "cfg3":
         W.update(n_users=10_000_000, m_items=2_000_000, n_interactions=625_000_000, d=128)
+    if args.workload == "cfg4":
+        W.update(n_users=10_000_000, m_items=2_000_000, n_interactions=625_000_000, d=64, layers=4, neg_size=256)
     cfg = dict(recdim=W["d"], layer=W["layers"], lr=W["lr"], decay=W["decay"],
                bpr_batch_size=W["batch"], device=dev, test_u_batch_size=10000, storage_dtype=args.storage,
                dist_exchange=args.exchange)
-    if args.workload in ("hbm", "cfg3"):
+    if args.workload in ("hbm", "cfg3", "cfg4"):
         from furusato_recommend_b200.dataloader import DeviceDataset
         n, m, tu, ti, su, si = bipartite(W["n_users"], W["m_items"], W["n_interactions"], seed=W["seed"], device=dev)
         ds = DeviceDataset(n, m, tu, ti, su, si, config=cfg)
@@ -199,7 +204,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         ds = BasicDataset(n, m, tu.numpy(), ti.numpy(), su.numpy(), si.numpy(), config=cfg, device=dev)
     torch.manual_seed(2020 + rank)
     K, d, B = W["layers"], W["d"], W["batch"]
-    if world == 1:
+    J = int(W.get("neg_size", 1))
+    if J > 1:
+        if world != 1:
+            raise SystemExit("cfg4 is measured on one GPU")
+        from furusato_recommend_b200 import LightGCNSSM
+        cfg["neg_size"] = J
+        model = LightGCNSSM(cfg, ds)   # reference arithmetic: the BPR softplus over J*B flat triples per step
+        model.train()
+        nnz = model.graph.nnz
+        fused = model._fused_step
+        launches_per_step = 2 * K + 2
+        B = B * J                      # rows per step (model/lgcnssm.py:141)
+    elif world == 1:
         model = LightGCN(cfg, ds)
         model.train()
         nnz = model.graph.nnz
@@ -213,7 +230,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         launches_per_step = 2 * K + 2
     N = n + m
 
-    S = UniformSample(ds, seed=CFG2["seed"], epoch=0, count=min(ds.trainDataSize, B * 512))
+    S = UniformSample(ds, neg_ratio=J, seed=CFG2["seed"], epoch=0,
+                      count=min(ds.trainDataSize, (B // J) * (512 if J == 1 else 4)))
     n_batches = len(S) // B
     users, pos, neg = (S[:, j].contiguous() for j in range(3))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -399,7 +417,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "scaling": "weak" if args.workload == "cfg2" else "strong", "vs_baseline": None,
             "dtype": "f32" if args.storage == "fp32" else "bf16-storage/f32-acc",
             "data": "synthetic",
-            "config": {"workload": f"{ {'hbm': 'hbm-bound', 'cfg3': 'cfg-3', 'cfg2': 'cfg-2'}[args.workload] }{' x%d' % world if world > 1 and args.workload == 'cfg2' else ''}: LightGCN {K}-layer d={d} BPR B={B} on a synthetic "
+            "config": {"workload": f"{ {'hbm': 'hbm-bound', 'cfg3': 'cfg-3', 'cfg2': 'cfg-2', 'cfg4': 'cfg-4 (lgcnssm, %d negatives per positive)' % J}[args.workload] }{' x%d' % world if world > 1 and args.workload == 'cfg2' else ''}: LightGCN {K}-layer d={d} BPR B={B} on a synthetic "
                                    f"five-core bipartite graph {n} users x {m} items, nnz(A_hat)={nnz}",
                        "l2": "256 MiB buffer written between timed steps (L2 flush, untimed)",
                        "parallelism": "1 GPU" if world == 1 else
@@ -435,6 +453,99 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ cfg-5: eval sweep
+def run_cfg5(args, rank: int, world: int, local_rank: int):
+    """BASELINE configs[4]: full-rank top-20 over 2M items, d=64, ~50 masked train positives per
+    user, users sharded over the ranks (independent units: no data-path collective; the item table
+    is replicated).  One step = score + mask + top-k of this rank's user shard (operand packing
+    included); value = users of all ranks / max-over-ranks time."""
+    import torch
+    import torch.distributed as dist
+    from furusato_recommend_b200 import ops
+
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    d, k, npos, m5 = 64, 20, 50, 2_000_000
+    U = args.eval_users // world
+    g5 = torch.Generator(device=dev).manual_seed(5 + rank)
+    gi = torch.Generator(device=dev).manual_seed(5)
+    ie = torch.randn(m5, d, generator=gi, device=dev) * 0.1           # same item table on every rank
+    ue = torch.randn(U, d, generator=g5, device=dev) * 0.1
+    ids = torch.arange(U, device=dev)
+    rp = torch.arange(U + 1, device=dev, dtype=torch.int64) * npos
+    pos = torch.empty((U, npos), dtype=torch.int32, device=dev)
+    for a in range(0, U, 1 << 20):                                     # bounded temporaries
+        b = min(U, a + (1 << 20))
+        pos[a:b] = torch.sort(torch.randint(0, m5, (b - a, npos), generator=g5, device=dev, dtype=torch.int32), dim=1)[0]
+    pos = pos.reshape(-1)
+    chunk = 148 * 128 * 8                                              # users per launch (8 CTA waves)
+
+    def step():
+        out = []
+        for a in range(0, U, chunk):
+            out.append(ops.score_topk(ue, ie, ids[a:a + chunk], rp, pos, k, precision="bf16")[0])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    t = e0.elapsed_time(e1) / 1e3 / steps
+    # e2e: host user ids in (pinned), top-k ids back on the host
+    hid = ids.cpu().pin_memory()
+    hout = torch.empty((U, k), dtype=torch.int32).pin_memory()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0.record()
+    for a in range(0, U, chunk):
+        did = hid[a:a + chunk].to(dev, non_blocking=True)
+        hout[a:a + chunk].copy_(ops.score_topk(ue, ie, did, rp, pos, k, precision="bf16")[0], non_blocking=True)
+    w1.record()
+    barrier()
+    t_e2e = w0.elapsed_time(w1) / 1e3
+    clk = clocks.stop()
+    if world > 1:
+        tt = torch.tensor([t, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t, t_e2e = float(tt[0]), float(tt[1])
+    if rank == 0:
+        _, peak_tf, which = measured_peaks()
+        flops = 2.0 * U * m5 * d
+        n_launch = (U + chunk - 1) // chunk
+        print(json.dumps({
+            "metric": "full-rank top-20 eval users/sec", "value": U * world / t, "unit": "users/s", "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16 operands / f32 accumulate (tcgen05)", "data": "synthetic",
+            "config": {"workload": f"cfg-5: full-rank top-{k} eval, {U * world} users x {m5} items, d={d}, {npos} masked "
+                                   f"train positives per user, users sharded over {world} GPU(s)",
+                       "l2": "operands (>= 256 MB item table) exceed L2; no flush needed",
+                       "parallelism": f"{world} GPU(s): user shards, item table replicated, no collective"},
+            "e2e": {"value": U * world / t_e2e, "unit": "users/s", "h2d_bytes_per_step": U * 8, "d2h_bytes_per_step": U * k * 4},
+            "gpu_launches": 3 * n_launch * steps,
+            "roofline": {"bound": "tensor", "kernel": "score_topk_tc_kernel", "achieved": flops / t / 1e12, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": flops / t / 1e12 / peak_tf, "traffic": None, "peak_source": which,
+                         "note": "2*U*m*d flops per rank; time includes the fp32->bf16 operand packing kernels"},
+            "clocks": clk}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -446,6 +557,9 @@ def main():
     if args.gpus != world:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    if args.workload == "cfg5":
+        run_cfg5(args, rank, world, local_rank)
+        return
     run_ours(args, rank, world, local_rank)
 
 
