@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "push", "nccl"],
                     help="N>1: push = all-gather fused into the SpMM epilogue over NVLink peer memory")
+    ap.add_argument("--partition", default="side_split", choices=["side_split", "two_sided"],
+                    help="N>1: side_split = users on the first N/2 ranks, items on the rest (a row is only sent to "
+                         "the other side); two_sided = every rank owns 1/N of both sides")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "hbm", "cfg3", "cfg4", "cfg5"],
                     help="hbm: 2.4M x 0.6M x 60M-edge graph, d=128 (table >> L2) for the honest HBM roofline; "
                          "cfg3: BASELINE configs[2], 10M x 2M x 500M edges, d=128 (graph built on device); "
@@ -191,7 +194,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         W.update(n_users=10_000_000, m_items=2_000_000, n_interactions=625_000_000, d=64, layers=4, neg_size=256)
     cfg = dict(recdim=W["d"], layer=W["layers"], lr=W["lr"], decay=W["decay"],
                bpr_batch_size=W["batch"], device=dev, test_u_batch_size=10000, storage_dtype=args.storage,
-               dist_exchange=args.exchange)
+               dist_exchange=args.exchange, dist_partition=args.partition)
     if args.workload in ("hbm", "cfg3", "cfg4"):
         from furusato_recommend_b200.dataloader import DeviceDataset
         n, m, tu, ti, su, si = bipartite(W["n_users"], W["m_items"], W["n_interactions"], seed=W["seed"], device=dev)
@@ -227,7 +230,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         model = DistLightGCN(cfg, ds, rank, world)
         nnz = ds.csr_graph().nnz
         fused = model.fused_step
-        launches_per_step = 2 * K + 2
+        # SpMM x 2K, BPR, Adam tick; push exchange adds 2 scale_rows_push + 1 exchange_rows_push
+        launches_per_step = 2 * K + 2 + (3 if model.exchange == "push" else 0)
     N = n + m
 
     S = UniformSample(ds, neg_ratio=J, seed=CFG2["seed"], epoch=0,
@@ -422,9 +426,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "l2": "256 MiB buffer written between timed steps (L2 flush, untimed)",
                        "parallelism": "1 GPU" if world == 1 else
                        f"{world} GPUs: rows partitioned by nnz; per-layer exchange = " +
-                       ("all-gather fused into the SpMM epilogue (NVLink peer stores, symmetric memory)"
-                        if getattr(model, "exchange", "") == "push" else "ncclAllGather") +
-                       " (2K per step) + one 3B-row all-reduce"},
+                       ("all-gather fused into the SpMM epilogue (NVLink peer stores, symmetric memory; "
+                        + ("bipartite side split: a row goes to the W/2 ranks of the other side only"
+                           if getattr(model.part, "side_split", False) else "every row to every rank")
+                        + ") (2K per step) + 3B-row exchange by owner peer stores; the whole step is one CUDA graph"
+                        if getattr(model, "exchange", "") == "push" else
+                        "ncclAllGather (2K per step) + one 3B-row all-reduce")},
             "e2e": {"value": nnz_total * K / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 3 * B * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps * 1e3},
             "gpu_launches": launches_per_step * args.steps,

@@ -61,6 +61,7 @@ SIGNATURES = {
     "lgcn_last_error": (C.c_char_p, []),
     "lgcn_propagate_layer": (C.c_int, [C.POINTER(GraphStruct), C.POINTER(LayerArgs), _P]),
     "lgcn_scale_rows_push": (C.c_int, [_P, _P, _I64, _I, _I, C.POINTER(C.c_void_p), _I, _I64, _P]),
+    "lgcn_exchange_rows_push": (C.c_int, [_P, _P, _I, _P, _I64, _I64, _I, C.POINTER(C.c_void_p), _I, _P]),
     "lgcn_bpr_fwd_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
     "lgcn_adam_tick": (C.c_int, [_P, _P, _D, _D, _D, _P]),
     "lgcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, _D, _D, _D, _P]),

@@ -476,6 +476,46 @@ extern "C" int lgcn_scale_rows_push(const float* x, const float* dinv, int64_t n
   return 0;
 }
 
+namespace lgcn {
+// rows[i] = [tab_a[loc_i] | tab_b[loc_i]] for the ids this rank owns, stored to EVERY peer's
+// [n_ids, width] buffer at row i.  Each id has exactly one owner, so after a barrier every rank
+// holds all rows without a reduction (the sync-free replacement of the 3B-row all-reduce).
+__global__ void __launch_bounds__(256)
+exchange_rows_push_kernel(const float* __restrict__ tab_a, const float* __restrict__ tab_b, int d4,
+                          const int64_t* __restrict__ padded_ids, int64_t n_ids, int64_t R, int rank,
+                          PeerPtrs peers, int n_peer) {
+  const int w4 = tab_b != nullptr ? 2 * d4 : d4;  // float4 per output row
+  const int64_t total = n_ids * w4;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / w4;
+    const int c = (int)(t - i * w4);
+    const int64_t id = __ldg(padded_ids + i);
+    if (id / R != rank) continue;
+    const int64_t loc = id - (int64_t)rank * R;
+    const float4 v = c < d4 ? ld_f4(tab_a + (loc * d4 + c) * 4) : ld_f4(tab_b + (loc * d4 + (c - d4)) * 4);
+    for (int q = 0; q < n_peer; ++q) st_f4(reinterpret_cast<float*>(peers.p[q]) + t * 4, v);
+  }
+}
+}  // namespace lgcn
+
+extern "C" int lgcn_exchange_rows_push(const float* tab_a, const float* tab_b, int d, const int64_t* padded_ids,
+                                       int64_t n_ids, int64_t rows_per_rank, int rank, void* const* dst_peers,
+                                       int n_dst_peers, lgcn_stream_t stream) {
+  LGCN_CHECK_ARG(tab_a && padded_ids && dst_peers, "null pointer argument");
+  LGCN_CHECK_ARG(n_dst_peers >= 1 && n_dst_peers <= LGCN_MAX_PEERS, "n_dst_peers out of range");
+  LGCN_CHECK_ARG(d > 0 && d % 4 == 0 && n_ids >= 0 && rows_per_rank > 0 && rank >= 0, "bad shape");
+  if (n_ids == 0) return 0;
+  lgcn::PeerPtrs pp;
+  for (int q = 0; q < LGCN_MAX_PEERS; ++q) pp.p[q] = q < n_dst_peers ? dst_peers[q] : nullptr;
+  const int64_t total = n_ids * (tab_b ? 2 : 1) * (d / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)lgcn::kSmCount * 16) blocks = (int64_t)lgcn::kSmCount * 16;
+  lgcn::exchange_rows_push_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      tab_a, tab_b, d / 4, padded_ids, n_ids, rows_per_rank, rank, pp, n_dst_peers);
+  LGCN_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int lgcn_abi_version(void) { return LGCN_ABI_VERSION; }
 extern "C" const char* lgcn_last_error(void) { return lgcn::last_error(); }
 

@@ -106,6 +106,18 @@ def scale_rows_push(x: torch.Tensor, dinv: torch.Tensor, dst_dtype: torch.dtype,
                                         dst_row_offset, _stream()), "lgcn_scale_rows_push")
 
 
+def exchange_rows_push(tab_a: torch.Tensor, tab_b: Optional[torch.Tensor], padded_ids: torch.Tensor,
+                       rows_per_rank: int, rank: int, dst_peers: Sequence[int]) -> None:
+    """Rows of the row-partitioned tables this rank owns -> row i of every peer's [n_ids, width] buffer."""
+    lib = _lib.load()
+    d = tab_a.shape[1]
+    arr = (C.c_void_p * len(dst_peers))(*dst_peers)
+    _lib.check(lib.lgcn_exchange_rows_push(_chk(tab_a, torch.float32, "tab_a"), _chk(tab_b, torch.float32, "tab_b", True),
+                                           d, _chk(padded_ids, torch.int64, "padded_ids"), padded_ids.numel(),
+                                           rows_per_rank, rank, arr, len(dst_peers), _stream()),
+               "lgcn_exchange_rows_push")
+
+
 def bpr_fwd_bwd(out: torch.Tensor, emb: torch.Tensor, users: torch.Tensor, pos: torch.Tensor,
                 neg: torch.Tensor, n_users: int, decay: float, G: torch.Tensor, cnt: torch.Tensor,
                 loss_out: torch.Tensor, work: torch.Tensor, work_counter: torch.Tensor,

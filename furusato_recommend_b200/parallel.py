@@ -38,19 +38,32 @@ class RowPartition:
     range of ITEM rows, each cut so that it carries 1/W of that side's edges: both the edges and
     the row count (epilogue + exchange volume) are balanced.  A single contiguous cut over
     [users | items] balances edges only — user blocks then hold 5x more rows than item blocks at
-    cfg-3 and their exchange traffic dominates (measured: 134 ms vs 463 ms on 8 GPUs)."""
+    cfg-3 and their exchange traffic dominates (measured: 134 ms vs 463 ms on 8 GPUs).
 
-    def __init__(self, rowptr: torch.Tensor, world: int, n_users: Optional[int] = None):
+    `side_split=True` (even world, n_users given) uses the bipartite structure instead: the first
+    W/2 ranks own ONLY user rows, the other W/2 ONLY item rows, each side cut into W/2 ranges of
+    equal edge count (both sides carry nnz/2 edges, so the SpMM work is still 1/W per rank).  A
+    user row's neighbours are all items and vice versa, so a rank never reads a row of its own
+    side: it needs just the OTHER side's table, and the per-layer exchange sends every row to W/2
+    ranks instead of W-1.  Ranks simply own an empty range on the other side (repeated cut
+    points), so owner / padded-id / shard logic is unchanged."""
+
+    def __init__(self, rowptr: torch.Tensor, world: int, n_users: Optional[int] = None, side_split: bool = False):
         N = rowptr.numel() - 1
         dev = rowptr.device
         self.world, self.n_nodes = world, N
         sides = [(0, N)] if n_users is None or n_users <= 0 or n_users >= N else [(0, n_users), (n_users, N)]
+        self.side_split = bool(side_split) and len(sides) == 2 and world % 2 == 0
         cuts = []
-        for lo, hi in sides:
+        for si, (lo, hi) in enumerate(sides):
+            pieces = world // 2 if self.side_split else world
             e0, e1 = int(rowptr[lo]), int(rowptr[hi])
-            targets = (e0 + torch.arange(1, world, device=dev, dtype=torch.float64) * ((e1 - e0) / world)).to(rowptr.dtype)
+            targets = (e0 + torch.arange(1, pieces, device=dev, dtype=torch.float64) * ((e1 - e0) / pieces)).to(rowptr.dtype)
             c = torch.searchsorted(rowptr[lo:hi + 1].contiguous(), targets, right=False).clamp_(0, hi - lo) + lo
             c = torch.cat([torch.full((1,), lo, dtype=c.dtype, device=dev), c, torch.full((1,), hi, dtype=c.dtype, device=dev)])
+            if self.side_split:   # empty ranges for the ranks of the other side
+                pad = torch.full((world // 2,), hi if si == 0 else lo, dtype=c.dtype, device=dev)
+                c = torch.cat([c, pad]) if si == 0 else torch.cat([pad, c])
             cuts.append(torch.cummax(c, 0)[0])
         self.cuts = cuts                                   # per side: [world + 1] global row boundaries
         self.side_lo = [lo for lo, _ in sides]
@@ -62,6 +75,13 @@ class RowPartition:
         for c in cuts[:-1]:
             self.side_off.append(self.side_off[-1] + (c[1:] - c[:-1]))
         self.starts = cuts[0]                               # kept for the single-range callers / tests
+
+    def readers_of(self, rank: int):
+        """Ranks whose local SpMM reads rows owned by `rank` (the targets of its per-layer push)."""
+        if not self.side_split:
+            return list(range(self.world))
+        half = self.world // 2
+        return list(range(half, self.world)) if rank < half else list(range(half))
 
     def _side(self, ids: torch.Tensor):
         if len(self.cuts) == 1:
@@ -210,9 +230,12 @@ class PushPropagator:
         self.part, self.rank, self.K, self.ops, self.graph = part, rank, n_layers, ops, graph
         self.dinv, self.storage_dtype = dinv_local, storage_dtype
         R, W = part.R, part.world
-        self.bufs = [symm.empty((W * R, d), dtype=storage_dtype, device=device) for _ in range(2)]
+        # zero-filled: rows nobody pushes (padding up to R; with the side-split partition also the
+        # whole own side) stay finite — the SpMM's padding slots re-read row 0 with weight 0
+        self.bufs = [symm.empty((W * R, d), dtype=storage_dtype, device=device).zero_() for _ in range(2)]
         self.hdl = [symm.rendezvous(t, group) for t in self.bufs]
-        self.peers = [[int(p) for p in h.buffer_ptrs] for h in self.hdl]
+        readers = part.readers_of(rank)   # side-split partition: only the other side's ranks
+        self.peers = [[int(h.buffer_ptrs[r]) for r in readers] for h in self.hdl]
         self.row0 = rank * R
 
     def _barrier(self):
@@ -271,7 +294,11 @@ class DistLightGCN:
         self.K = int(config["layer"])
         self.device = torch.device(config["device"])
         g = dataset.csr_graph()
-        self.part = RowPartition(g.rowptr, world, n_users=self.n)
+        # bipartite side split (users on the first W/2 ranks, items on the rest) halves the exchange
+        # when the two sides have comparable row counts; cfg "dist_partition": "two_sided" keeps
+        # every rank on both sides
+        mode_p = config.get("dist_partition", "side_split")
+        self.part = RowPartition(g.rowptr, world, n_users=self.n, side_split=(mode_p == "side_split"))
         rp, colp, dl = self.part.local_csr(rank, g.rowptr, g.col, g.dinv)
         self.local_graph = CsrGraph(self.part.rows[rank], 0, rp, colp, dl, **decompose_rows(rp))
         self.local_nnz = int(colp.numel())
@@ -307,8 +334,12 @@ class DistLightGCN:
             self.prop = DistPropagator(self.part, rank, dl, self.K, self._local_spmm, group, storage)
         self.collectives_per_step = 2 * self.K + 1
         self._ar = None
-        # capturing NCCL collectives into a CUDA graph deadlocked on the 2-GPU box (round 1); opt-in only
-        self.use_cuda_graph = bool(config.get("dist_cuda_graph", False))
+        self._xbuf = None
+        # Capturing NCCL collectives into a CUDA graph deadlocked on the 2-GPU box (round 1), so the
+        # NCCL exchange stays eager unless asked.  The push exchange has no NCCL call on the step at
+        # all (layers AND the 3B-row exchange go through peer stores + symmetric-memory barriers,
+        # which are plain kernels), so its step is captured by default.
+        self.use_cuda_graph = bool(config.get("dist_cuda_graph", self.exchange == "push"))
         self._graph = None
 
     def load_global_embedding(self, E: torch.Tensor) -> None:
@@ -367,8 +398,12 @@ class DistLightGCN:
         ops, part, B = self.ops, self.part, users.numel()
         self.prop.forward(self.emb, self.acc, self.out)
         ids = part.to_padded(torch.cat([users, pos + self.n, neg + self.n]))
-        # one all-reduce for both the propagated and the ego rows: [3B, 2d]
-        both, mine = exchange_rows(part, self.rank, [self.out, self.emb], ids, self.group)
+        if self.exchange == "push":
+            # owners store [out | emb] rows straight into every rank's [3B, 2d] buffer over NVLink
+            both, mine = self._exchange_rows_push(ids)
+        else:
+            # one all-reduce for both the propagated and the ego rows: [3B, 2d]
+            both, mine = exchange_rows(part, self.rank, [self.out, self.emb], ids, self.group)
         out_c, emb_c = both[:, :self.d].contiguous(), both[:, self.d:].contiguous()
         if self._ar is None or self._ar.numel() != B:
             self._ar = torch.arange(B, device=self.device, dtype=torch.int64)
@@ -389,6 +424,24 @@ class DistLightGCN:
                            emb=self.emb, adam_m=self.m1, adam_v=self.v1, adam_hp=self.hp, zero_base=False)
         self.G.zero_()
         return self.loss_out[2]
+
+    def _exchange_rows_push(self, ids: torch.Tensor):
+        """(rows [3B, 2d], mine [3B]) with the rows written by their owners through peer mappings.
+        No barrier is needed BEFORE the stores: a peer can only be here after the barriers of this
+        step's forward pass, which every rank enters after it finished reading the previous step's
+        rows.  One barrier after the stores publishes them."""
+        import torch.distributed._symmetric_memory as symm
+        n_ids = ids.numel()
+        if self._xbuf is None or self._xbuf.shape[0] != n_ids:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("exchange buffer must exist before graph capture")
+            self._xbuf = symm.empty((n_ids, 2 * self.d), dtype=torch.float32, device=self.device)
+            self._xhdl = symm.rendezvous(self._xbuf, self.group if self.group is not None else dist.group.WORLD)
+            self._xpeers = [int(p) for p in self._xhdl.buffer_ptrs]
+        self.ops.exchange_rows_push(self.out, self.emb, ids, self.part.R, self.rank, self._xpeers)
+        self._xhdl.barrier(channel=1)
+        mine = torch.div(ids, self.part.R, rounding_mode="floor") == self.rank
+        return self._xbuf, mine
 
     def gather_out(self) -> torch.Tensor:
         """Global light_out [N, d] on every rank (eval: the item table is replicated)."""

@@ -95,6 +95,8 @@ typedef struct lgcn_graph {
  *           cnt[i] = 0 and, if zero_base, base[i] = 0 (so the next step starts
  *           clean; zero_base is illegal when src == base, i.e. K == 1)
  * ------------------------------------------------------------------------ */
+/* SRC contract: row 0 of `src` must hold finite values — gather slots past the end of a
+ * neighbour list re-read it (an L1 hit, no predicate on the load) and add it with weight 0. */
 typedef struct lgcn_layer_args {
   int d;               /* embedding width                                       */
   int src_dtype;       /* LGCN_F32 | LGCN_BF16                                  */
@@ -140,6 +142,15 @@ int lgcn_propagate_layer(const lgcn_graph_t* g /*HOST*/, const lgcn_layer_args_t
 int lgcn_scale_rows_push(const float* x, const float* dinv, int64_t n_rows, int d, int dst_dtype,
                          void* const* dst_peers /*HOST array*/, int n_dst_peers,
                          int64_t dst_row_offset, lgcn_stream_t stream);
+
+/* Row exchange of the partitioned BPR step (the getEmbedding gathers of model/lgcn.py:88-96 when
+ * the table is row-partitioned): for every i with padded_ids[i] / rows_per_rank == rank, the row
+ * [tab_a[loc] | tab_b[loc]] (loc = padded_ids[i] % rows_per_rank; tab_b may be NULL) is stored to
+ * row i of EVERY peer buffer ([n_ids, 2d] or [n_ids, d] fp32, peer-mapped).  Each id has one owner,
+ * so after a cross-GPU barrier all ranks hold all rows; no reduction, no NCCL call. */
+int lgcn_exchange_rows_push(const float* tab_a, const float* tab_b, int d, const int64_t* padded_ids,
+                            int64_t n_ids, int64_t rows_per_rank, int rank,
+                            void* const* dst_peers /*HOST array*/, int n_dst_peers, lgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Fused BPR forward + backward seed.  Replaces getEmbedding + bpr_loss

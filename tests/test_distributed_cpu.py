@@ -41,7 +41,7 @@ def _cpu_local_spmm(rp, col, dinv):
     return f
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, side_split=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -49,7 +49,11 @@ def _worker(rank, world, port, ret):
         n, m = int(g["n_users"]), int(g["m_items"])
         K = int(g["config"][1])
         csr = G.build_csr_graph(n, m, torch.from_numpy(g["train_user"]), torch.from_numpy(g["train_item"]))
-        part = RowPartition(csr.rowptr, world, n_users=n if os.environ.get("LGCN_TEST_TWO_SIDED", "1") == "1" else None)
+        part = RowPartition(csr.rowptr, world, n_users=n if os.environ.get("LGCN_TEST_TWO_SIDED", "1") == "1" else None,
+                            side_split=side_split)
+        if side_split:  # rank 0 owns users only, rank 1 items only; each pushes to the other side only
+            assert part.side_split and part.readers_of(rank) == [1 - rank]
+            assert part.ranges(0)[1][0] == part.ranges(0)[1][1] and part.ranges(1)[0][0] == part.ranges(1)[0][1]
         rp, colp, dl = part.local_csr(rank, csr.rowptr, csr.col, csr.dinv)
         prop = DistPropagator(part, rank, dl, K, _cpu_local_spmm(rp, colp, dl))
         E = torch.from_numpy(g["E0"])
@@ -111,18 +115,34 @@ def test_row_partition_indexing(n_users):
             assert rp.numel() == p.rows[r] + 1 and int(rp[-1]) == colp.numel() and dl.numel() == p.R
             tot += colp.numel()
         assert tot == 40
+    if n_users is not None:  # side split: users on the first W/2 ranks, items on the rest
+        for world in (2, 4):
+            p = RowPartition(rowptr, world, n_users=n_users, side_split=True)
+            assert p.side_split and sum(p.rows) == 8
+            ids = torch.arange(8)
+            pad, own = p.to_padded(ids), p.owner(ids)
+            assert len(torch.unique(pad)) == 8 and torch.equal(own, pad // p.R)
+            assert bool((own[:n_users] < world // 2).all()) and bool((own[n_users:] >= world // 2).all())
+            x = torch.arange(16.0).reshape(8, 2)
+            gathered = torch.cat([p.shard(r, x) for r in range(world)])
+            assert torch.equal(p.unshard(gathered), x) and torch.equal(gathered[pad], x)
+            assert p.readers_of(0) == list(range(world // 2, world)) and p.readers_of(world - 1) == list(range(world // 2))
+            col = torch.arange(40, dtype=torch.int32) % 8
+            assert sum(p.local_csr(r, rowptr, col, torch.ones(8))[1].numel() for r in range(world)) == 40
+        assert not RowPartition(rowptr, 3, n_users=n_users, side_split=True).side_split   # odd world: falls back
     if n_users is not None:  # two-sided: both sides are cut separately, rows stay balanced
         p = RowPartition(rowptr, 2, n_users=n_users)
         assert len(p.cuts) == 2 and p.cuts[0][0] == 0 and p.cuts[0][-1] == 3 and p.cuts[1][0] == 3 and p.cuts[1][-1] == 8
 
 
 @pytest.mark.timeout(300)
-def test_partitioned_propagation_world2_gloo():
+@pytest.mark.parametrize("side_split", [False, True])
+def test_partitioned_propagation_world2_gloo(side_split):
     world = 2
     port = _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, ret, side_split), nprocs=world, join=True)
         assert len(ret) == world
         for rank in range(world):
             err_f, err_b, err_x, n_mine, R, starts = ret[rank]

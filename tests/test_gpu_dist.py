@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, ret, exchange="auto"):
+def _worker(rank, world, port, ret, exchange="auto", partition="side_split"):
     import torch.distributed as dist
     from furusato_recommend_b200 import LightGCN
     from furusato_recommend_b200.dataloader import BasicDataset
@@ -33,7 +33,7 @@ def _worker(rank, world, port, ret, exchange="auto"):
         d, K, B = (int(x) for x in g["config"])
         lr, decay = (float(x) for x in g["hyper"])
         cfg = dict(recdim=d, layer=K, lr=lr, decay=decay, bpr_batch_size=B, device=dev, test_u_batch_size=128,
-                   dist_exchange=exchange)
+                   dist_exchange=exchange, dist_partition=partition)
         ds = BasicDataset(int(g["n_users"]), int(g["m_items"]), g["train_user"], g["train_item"], g["test_user"],
                           g["test_item"], config=cfg, device=dev)
         E0 = torch.from_numpy(g["E0"]).to(dev)
@@ -70,14 +70,16 @@ def _gather(dm, local):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("exchange", ["nccl", "push"])
+@pytest.mark.parametrize("exchange,partition", [("nccl", "two_sided"), ("push", "two_sided"), ("push", "side_split"),
+                                                ("nccl", "side_split")])
 @pytest.mark.timeout(120)
-def test_row_partitioned_training_matches_reference_2gpu(exchange):
-    """nccl: ncclAllGather per layer; push: all-gather fused into the SpMM epilogue (NVLink peer stores)."""
+def test_row_partitioned_training_matches_reference_2gpu(exchange, partition):
+    """nccl: ncclAllGather per layer; push: all-gather fused into the SpMM epilogue (NVLink peer stores) and
+    the whole step replayed as one CUDA graph.  side_split: users on rank 0, items on rank 1."""
     world, port = 2, _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, ret, exchange), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, ret, exchange, partition), nprocs=world, join=True)
         for rank in range(world):
             e_prop, l1, l2, e_emb, same, g1, g2, used = ret[rank]
             assert used == exchange
