@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "push", "nccl"],
                     help="N>1: push = all-gather fused into the SpMM epilogue over NVLink peer memory")
-    ap.add_argument("--partition", default="side_split", choices=["side_split", "two_sided"],
+    ap.add_argument("--partition", default="auto", choices=["auto", "side_split", "two_sided"],
                     help="N>1: side_split = users on the first N/2 ranks, items on the rest (a row is only sent to "
                          "the other side); two_sided = every rank owns 1/N of both sides")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "hbm", "cfg3", "cfg4", "cfg5"],
