@@ -31,6 +31,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <string>
+
 #include "common.cuh"
 
 namespace lgcn {
@@ -120,6 +122,12 @@ __device__ __forceinline__ void tc_ld32_pack16(uint32_t taddr, uint32_t (&r)[32]
         "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
         "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
+}
+// one column: every lane gets its own row's value (used to re-read a candidate from TMEM)
+__device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+  return v;
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -286,14 +294,26 @@ struct Params {
   int32_t* out_idx;
   float* out_val;
   float* dense;            // optional [n_eval, m_items] dump of the accumulators (tests)
-  int debug_mode;          // 0 = normal; 1 = epilogue skips the TMEM reads (pipeline experiments)
+  int debug_mode;          // 0 = normal; pipeline experiments: 1 = epilogue skips the TMEM reads,
+                           // 2 = TMEM reads only, 3 = reads + max tree, no candidate passes
   int acc16;               // 1: f16 accumulators, read back two per register (tcgen05.ld pack::16b)
 };
 
-template <int D, int TN, int GROUPS, bool DUMP, bool ACC16>
+// MT user tiles (128 rows each) share every item tile: the B operand stream is what bounds the MMA
+// pipeline at d = 64 (L2 -> SM bulk-copy bandwidth, ~43 B/clk/SM chip-wide: a 32 KB tile per 512
+// MMA clocks does not fit), so MT = 2 halves the bytes per flop.  GROUPS epilogue groups of 4 warps:
+// group g works on user tile g / CG, column slice g % CG of every item tile (CG = GROUPS / MT).
+// NST accumulator stages in TMEM: an epilogue warp that runs into candidates (the rare slow path)
+// only holds back ITS stage; with 4 stages the other warps and the MMA issuer run ahead and the
+// variance averages out instead of costing every tile the slowest warp's time.
+template <int D, int TN, int GROUPS, bool DUMP, bool ACC16, int MT, int NST>
 __global__ void __launch_bounds__((kFrontWarps + 4 * GROUPS) * 32, 1)
 score_topk_tc_kernel(const Params p) {
   constexpr int NT = GROUPS * 128;              // epilogue threads
+  constexpr int CG = GROUPS / MT;               // column groups per user tile
+  constexpr int kTmemCols = NST * MT * TN;
+  static_assert(GROUPS % MT == 0 && kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32,
+                "TMEM holds NST stages x MT accumulators of TN columns (power of two, <= 512)");
   constexpr uint32_t kABytes = kUM * D * 2;
   constexpr uint32_t kBBytes = TN * D * 2;
   constexpr int kKSteps = D / 16;
@@ -302,18 +322,18 @@ score_topk_tc_kernel(const Params p) {
 
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;
-  unsigned char* sB = sA + kABytes;
+  unsigned char* sB = sA + MT * kABytes;
   float* cval = reinterpret_cast<float*>(sB + (size_t)p.stages * kBBytes);
   int* cidx = reinterpret_cast<int*>(cval + (size_t)p.cap * NT);
   int* ccnt = cidx + (size_t)p.cap * NT;                      // [NT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ccnt + NT);    // 8-byte aligned: all sizes are multiples of 8
-  // bars: full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2], afull
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+  // bars: full[kMaxStages], empty[kMaxStages], tfull[kMaxStages], tempty[kMaxStages], afull
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
-  const uint32_t bar_tfull = smem_u32(bars + 2 * kMaxStages), bar_tempty = smem_u32(bars + 2 * kMaxStages + 2);
-  const uint32_t bar_afull = smem_u32(bars + 2 * kMaxStages + 4);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * kMaxStages), bar_tempty = smem_u32(bars + 3 * kMaxStages);
+  const uint32_t bar_afull = smem_u32(bars + 4 * kMaxStages);
   const int n_tiles = (p.m_items + TN - 1) / TN;
   const int S = p.stages;
 
@@ -322,7 +342,7 @@ score_topk_tc_kernel(const Params p) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NST; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, 128 * GROUPS);
     }
@@ -331,7 +351,7 @@ score_topk_tc_kernel(const Params p) {
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(2 * TN));
+                 "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -342,9 +362,9 @@ score_topk_tc_kernel(const Params p) {
   if (warp == 0) {
     // ------------------------------------------------ producer
     if (lane == 0) {
-      mbar_expect_tx(bar_afull, kABytes);
-      bulk_g2s(smem_u32(sA), reinterpret_cast<const unsigned char*>(p.a_packed) + (size_t)blockIdx.x * kABytes,
-               kABytes, bar_afull);
+      mbar_expect_tx(bar_afull, MT * kABytes);   // the CTA's MT user tiles are contiguous in a_packed
+      bulk_g2s(smem_u32(sA), reinterpret_cast<const unsigned char*>(p.a_packed) + (size_t)blockIdx.x * MT * kABytes,
+               MT * kABytes, bar_afull);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % S;
         if (j >= S) mbar_wait(bar_empty + 8 * s, ((j / S) - 1) & 1);
@@ -361,19 +381,22 @@ score_topk_tc_kernel(const Params p) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
       mbar_wait(bar_afull, 0);
-      const uint64_t adesc0 = make_desc(smem_u32(sA), kUM * 16, 128);
       for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % S, a = j & 1;
-        if (j >= 2) mbar_wait(bar_tempty + 8 * a, ((j >> 1) - 1) & 1);
+        const int s = j % S, a = j % NST;
+        if (j >= NST) mbar_wait(bar_tempty + 8 * a, ((j / NST) - 1) & 1);
         mbar_wait(bar_full + 8 * s, (j / S) & 1);
         tc_fence_after();
         const uint64_t bdesc0 = make_desc(smem_u32(sB + (size_t)s * kBBytes), TN * 16, 128);
 #pragma unroll
-        for (int kk = 0; kk < kKSteps; ++kk) {
-          // one K=16 step = two 16-byte k-chunks = 2*LBO bytes further along
-          const uint64_t ad = adesc0 + (uint64_t)((kk * 2 * kUM * 16) >> 4);
-          const uint64_t bd = bdesc0 + (uint64_t)((kk * 2 * TN * 16) >> 4);
-          tc_mma_bf16(tmem_base + a * TN, ad, bd, kIdesc, kk > 0 ? 1u : 0u);
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t adesc0 = make_desc(smem_u32(sA + (size_t)mt * kABytes), kUM * 16, 128);
+#pragma unroll
+          for (int kk = 0; kk < kKSteps; ++kk) {
+            // one K=16 step = two 16-byte k-chunks = 2*LBO bytes further along
+            const uint64_t ad = adesc0 + (uint64_t)((kk * 2 * kUM * 16) >> 4);
+            const uint64_t bd = bdesc0 + (uint64_t)((kk * 2 * TN * 16) >> 4);
+            tc_mma_bf16(tmem_base + (a * MT + mt) * TN, ad, bd, kIdesc, kk > 0 ? 1u : 0u);
+          }
         }
         tc_commit(bar_empty + 8 * s);   // smem stage reusable once these MMAs retire
         tc_commit(bar_tfull + 8 * a);   // accumulator stage ready for the epilogue
@@ -386,7 +409,8 @@ score_topk_tc_kernel(const Params p) {
     const int q = warp & 3;                       // TMEM sub-partition this warp may read
     const int row = 32 * q + lane;                // row inside the user tile == TMEM lane
     const int t = grp * 128 + row;                // slot in the candidate arrays
-    const int64_t grow = (int64_t)blockIdx.x * kUM + row;
+    const int mt = grp / CG, cg = grp % CG;       // user tile and column slice of this group
+    const int64_t grow = ((int64_t)blockIdx.x * MT + mt) * kUM + row;
     const bool live = grow < p.n_eval;
     const int32_t* my_pos = p.pos_sorted;
     int my_npos = 0;
@@ -399,10 +423,12 @@ score_topk_tc_kernel(const Params p) {
     float* mv = cval + t;
     int* mi = cidx + t;
     Sel sel;
-    sel.thr = live ? -INFINITY : INFINITY;
+    sel.thr = (live && p.debug_mode < 3) ? -INFINITY : INFINITY;   // debug 3: max tree only, no candidate ever passes
     sel.cnt = 0;
     sel.sorted = 0;
-    const int trig = p.cap - 12;
+    // warp-synchronous compaction once any lane's buffer is nearly full; with the small buffers of
+    // the 4-group layout keep at least k + 8 (or cap - 4) entries before folding
+    const int trig = max(p.cap - 12, min(p.cap - 4, p.k + 8));
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     // walk of the user's sorted train positives, in step with the item sweep
     int pp = 0;
@@ -410,15 +436,16 @@ score_topk_tc_kernel(const Params p) {
     // both epilogue groups work on every tile; group g owns the chunks [g*CPG, (g+1)*CPG).
     // A chunk is one tcgen05.ld: 32 fp32 columns, or 64 packed f16 columns (ACC16).
     constexpr int COLS = ACC16 ? 64 : 32;
-    constexpr int CPG = TN / COLS / GROUPS;
-    const int c0 = grp * CPG;
+    constexpr int CPG = TN / COLS / CG;
+    static_assert(CPG >= 1 && CPG * COLS * CG == TN, "every epilogue group needs whole chunks of the tile");
+    const int c0 = cg * CPG;
 
     for (int j = 0; j < n_tiles; ++j) {
-      const int a = j & 1;
-      mbar_wait(bar_tfull + 8 * a, (j >> 1) & 1);
+      const int a = j % NST;
+      mbar_wait(bar_tfull + 8 * a, (j / NST) & 1);
       tc_fence_after();
       const int item_tile0 = j * TN + c0 * COLS;
-      const uint32_t tbase = tmem_base + lane_base + (uint32_t)(a * TN + c0 * COLS);
+      const uint32_t tbase = tmem_base + lane_base + (uint32_t)((a * MT + mt) * TN + c0 * COLS);
 #pragma unroll 1
       for (int cc = 0; cc < (p.debug_mode == 1 ? 0 : CPG); ++cc) {
         uint32_t r[32];
@@ -426,6 +453,10 @@ score_topk_tc_kernel(const Params p) {
         if (ACC16) tc_ld32_pack16(tbase + (uint32_t)(cc * COLS), r);
         else tc_ld32(tbase + (uint32_t)(cc * COLS), r);
         tc_wait_ld();
+        if (p.debug_mode == 2) {   // pipeline experiment: TMEM reads only, no selection work
+          if ((r[0] ^ r[31]) == 0x7fc12345u) sel.cnt = 1;
+          continue;
+        }
         const int item0 = item_tile0 + cc * COLS;
         if (DUMP) {
           if (live) {
@@ -440,30 +471,84 @@ score_topk_tc_kernel(const Params p) {
             }
           }
         }
-        float m4[4];
-        if ((ACC16 ? max32_h(r, m4) : max32(r, m4)) > sel.thr) {
+        if (!ACC16) {
+          // Fast path: one max tree per 32 scores against the row's threshold.  Slow path (some lane
+          // of the warp has a candidate): build the per-lane hit mask — after this r[] is dead, so
+          // nothing has to be kept alive across the candidate handling — then walk the columns any
+          // lane hit in ascending order, RE-READING that column from TMEM (a 1-register tcgen05.ld,
+          // ~40 clk; the accumulator stage is still ours) instead of indexing 32 live registers.
+          float m4[4];
+          const float cm = max32(r, m4);
+          if (__any_sync(0xffffffffu, cm > sel.thr)) {
+            // per-lane hit mask, built only for the 8-column blocks some lane of the warp hit
+            uint32_t hm = 0;
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            if (m4[b] > sel.thr) {
+            for (int b = 0; b < 4; ++b) {
+              if (__any_sync(0xffffffffu, m4[b] > sel.thr)) {
 #pragma unroll
-              for (int i = 8 * b; i < 8 * b + 8; ++i) {
-#pragma unroll
-                for (int h = 0; h < (ACC16 ? 2 : 1); ++h) {
-                  const float v = ACC16 ? (h == 0 ? h2_lo(r[i]) : h2_hi(r[i])) : __uint_as_float(r[i]);
+                for (int i = 8 * b; i < 8 * b + 8; ++i) hm |= (__uint_as_float(r[i]) > sel.thr) ? (1u << i) : 0u;
+              }
+            }
+            uint32_t any = __reduce_or_sync(0xffffffffu, hm);
+            // one candidate of this lane: positives walk, mask, append (ascending item ids)
+            auto take = [&](int c, uint32_t raw) {
+              if ((hm >> c) & 1u) {
+                const int item = item0 + c;
+                while (next_pos < item) {   // walk of the sorted train positives (ascending sweep)
+                  ++pp;
+                  next_pos = pp < my_npos ? __ldg(my_pos + pp) : 0x7fffffff;
+                }
+                const float v = next_pos == item ? p.mask_value : __uint_as_float(raw);  // trainer.py:137
+                if (item < p.m_items && v > sel.thr) {   // item >= m_items: zero padding of the last tile
+                  if (sel.cnt == p.cap) sel = sel_compact(sel, mv, mi, NT, p.k);  // rare: threshold still -inf
                   if (v > sel.thr) {
-                    const SelWalk w = sel_append(sel, pp, next_pos, my_pos, my_npos, v,
-                                                 ACC16 ? item0 + 2 * i + h : item0 + i, p.m_items,
-                                                 p.mask_value, mv, mi, NT, p.cap, p.k);
-                    sel = w.s;
-                    pp = w.pp;
-                    next_pos = w.next;
+                    mv[sel.cnt * NT] = v;
+                    mi[sel.cnt * NT] = item;
+                    ++sel.cnt;
+                  }
+                }
+              }
+            };
+            while (any) {   // two columns per round: both re-reads are in flight before the one wait
+              const int ca = __ffs(any) - 1;
+              any &= any - 1;
+              const bool two = any != 0;
+              const int cb = two ? __ffs(any) - 1 : ca;
+              any &= any - 1;   // no-op when any == 0
+              __syncwarp();     // the candidate handling below diverges; tcgen05.ld is warp-collective
+              const uint32_t ra = tc_ld1(tbase + (uint32_t)(cc * COLS + ca));
+              const uint32_t rb = tc_ld1(tbase + (uint32_t)(cc * COLS + cb));
+              tc_wait_ld();
+              take(ca, ra);
+              if (two) take(cb, rb);
+            }
+            if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
+          }
+        } else {
+          float m4[4];
+          if (max32_h(r, m4) > sel.thr) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              if (m4[b] > sel.thr) {
+#pragma unroll
+                for (int i = 8 * b; i < 8 * b + 8; ++i) {
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const float v = h == 0 ? h2_lo(r[i]) : h2_hi(r[i]);
+                    if (v > sel.thr) {
+                      const SelWalk w = sel_append(sel, pp, next_pos, my_pos, my_npos, v, item0 + 2 * i + h,
+                                                   p.m_items, p.mask_value, mv, mi, NT, p.cap, p.k);
+                      sel = w.s;
+                      pp = w.pp;
+                      next_pos = w.next;
+                    }
                   }
                 }
               }
             }
           }
+          if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
         }
-        if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * a);
@@ -471,25 +556,32 @@ score_topk_tc_kernel(const Params p) {
 
     sel = sel_compact(sel, mv, mi, NT, p.k);
     ccnt[t] = sel.cnt;
-    if (GROUPS == 2) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-    if (grp == 0 && live) {
-      const int na = sel.cnt;
-      const int nb = GROUPS == 2 ? ccnt[t + 128] : 0;
-      const float* bv = cval + t + 128;
-      const int* bi = cidx + t + 128;
-      int ia = 0, ib = 0;
+    if (GROUPS > 1) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+    if (cg == 0 && live) {
+      // merge the CG sorted partial lists of this row (the column slices of its user tile) by
+      // (value desc, item id asc); slice g of this row lives in slot t + 128 * g
+      int head[CG], num[CG];
+#pragma unroll
+      for (int g = 0; g < CG; ++g) {
+        head[g] = 0;
+        num[g] = g == 0 ? sel.cnt : ccnt[t + 128 * g];
+      }
       for (int o = 0; o < p.k; ++o) {
-        const bool ha = ia < na, hb = ib < nb;
         float v = -INFINITY;
-        int id = -1;
-        if (ha || hb) {
-          const float va = ha ? mv[ia * NT] : 0.f, vb = hb ? bv[ib * NT] : 0.f;
-          const int xa = ha ? mi[ia * NT] : 0, xb = hb ? bi[ib * NT] : 0;
-          const bool take_a = ha && (!hb || va > vb || (va == vb && xa < xb));
-          if (take_a) { v = va; id = xa; ++ia; } else { v = vb; id = xb; ++ib; }
+        int id = -1, from = -1;
+#pragma unroll
+        for (int g = 0; g < CG; ++g) {
+          if (head[g] < num[g]) {
+            const float vg = cval[head[g] * NT + t + 128 * g];
+            const int xg = cidx[head[g] * NT + t + 128 * g];
+            if (from < 0 || vg > v || (vg == v && xg < id)) { v = vg; id = xg; from = g; }
+          }
         }
+#pragma unroll
+        for (int g = 0; g < CG; ++g)
+          if (g == from) ++head[g];
         p.out_idx[grow * p.k + o] = id;
-        p.out_val[grow * p.k + o] = v;
+        p.out_val[grow * p.k + o] = from < 0 ? -INFINITY : v;
       }
     }
   }
@@ -499,51 +591,63 @@ score_topk_tc_kernel(const Params p) {
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
 
-template <int D, int TN, int GROUPS>
+template <int D, int TN, int GROUPS, int MT, int NST>
 static int launch(const Params& p0, cudaStream_t st) {
   Params p = p0;
   constexpr int NT = GROUPS * 128;
-  const size_t a_bytes = (size_t)kUM * D * 2, b_bytes = (size_t)TN * D * 2;
+  const size_t a_bytes = (size_t)MT * kUM * D * 2, b_bytes = (size_t)TN * D * 2;
   const size_t cand = (size_t)p.cap * NT * 8 + (size_t)NT * 4;
-  const size_t tail = (2 * 8 + 5) * 8 + 16;
+  const size_t tail = (4 * 8 + 1) * 8 + 16;
   if (a_bytes + cand + tail + 2 * b_bytes > kSmemLimit) {
     set_last_error("k=%d does not fit the tensor-core top-k shared-memory budget", p.k);
     return LGCN_ERR_UNSUPPORTED;
   }
   int stages = (int)((kSmemLimit - a_bytes - cand - tail) / b_bytes);
-  if (stages > 4) stages = 4;
+  if (stages > 8) stages = 8;   // kMaxStages barriers
   p.stages = stages;
   const size_t smem = a_bytes + (size_t)stages * b_bytes + cand + tail;
-  const int grid = (p.n_eval + kUM - 1) / kUM;
+  const int grid = (p.n_eval + kUM * MT - 1) / (kUM * MT);
   const int threads = (kFrontWarps + 4 * GROUPS) * 32;
 #define LGCN_TC_LAUNCH(DUMP_, ACC_)                                                                     \
   do {                                                                                                    \
-    auto kern = score_topk_tc_kernel<D, TN, GROUPS, DUMP_, ACC_>;                                         \
+    auto kern = score_topk_tc_kernel<D, TN, GROUPS, DUMP_, ACC_, MT, NST>;                                \
     LGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     kern<<<grid, threads, smem, st>>>(p);                                                                 \
   } while (0)
-  if (p.dense != nullptr) {
-    if (p.acc16) LGCN_TC_LAUNCH(true, true); else LGCN_TC_LAUNCH(true, false);
+  constexpr bool kAcc16Ok = (TN / 64) % (GROUPS / MT) == 0;   // a group needs whole 64-column chunks
+  if (p.acc16) {
+    if constexpr (kAcc16Ok) {
+      if (p.dense != nullptr) LGCN_TC_LAUNCH(true, true); else LGCN_TC_LAUNCH(false, true);
+    } else {
+      set_last_error("f16 accumulators need TN/64 divisible by the column groups per user tile");
+      return LGCN_ERR_UNSUPPORTED;
+    }
   } else {
-    if (p.acc16) LGCN_TC_LAUNCH(false, true); else LGCN_TC_LAUNCH(false, false);
+    if (p.dense != nullptr) LGCN_TC_LAUNCH(true, false); else LGCN_TC_LAUNCH(false, false);
   }
 #undef LGCN_TC_LAUNCH
   LGCN_LAUNCH_OK();
   return 0;
 }
 
-template <int D, int TN>
-static int run(const float* user_emb, const float* item_emb, const int64_t* user_ids, int n_eval,
-               int m_items, const int64_t* pos_rowptr, const int32_t* pos_sorted, int k,
-               float mask_value, int32_t* out_idx, float* out_val, float* dense, void* workspace,
-               size_t workspace_bytes, int acc16, cudaStream_t st) {
-  const int64_t n_ut = (n_eval + kUM - 1) / kUM, n_it = ((int64_t)m_items + TN - 1) / TN;
+static size_t smem_need(int d, int tn, int groups, int mt, int cap) {
+  return (size_t)mt * kUM * d * 2 + (size_t)cap * groups * 128 * 8 + (size_t)groups * 128 * 4 + (4 * 8 + 1) * 8 + 16 +
+         2 * (size_t)tn * d * 2;
+}
+
+// One configuration: pack both operands for (TN, MT) and launch.
+template <int D, int TN, int GROUPS, int MT, int NST>
+static int run_cfg(const float* user_emb, const float* item_emb, const int64_t* user_ids, int n_eval,
+                   int m_items, const int64_t* pos_rowptr, const int32_t* pos_sorted, int k, int cap,
+                   float mask_value, int32_t* out_idx, float* out_val, float* dense, void* workspace,
+                   size_t workspace_bytes, int acc16, cudaStream_t st) {
+  const int64_t n_ut = ((n_eval + kUM * MT - 1) / (kUM * MT)) * MT, n_it = ((int64_t)m_items + TN - 1) / TN;
   const size_t a_total = (size_t)n_ut * kUM * D * 2, b_total = (size_t)n_it * TN * D * 2;
   if (workspace == nullptr || workspace_bytes < a_total + b_total) {
     set_last_error("score_topk (bf16) needs a %zu-byte workspace, got %zu", a_total + b_total,
@@ -578,17 +682,47 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
   Params p;
   p.a_packed = a_packed; p.b_packed = b_packed; p.user_ids = user_ids;
   p.n_eval = n_eval; p.m_items = m_items; p.pos_rowptr = pos_rowptr; p.pos_sorted = pos_sorted;
-  p.k = k; p.mask_value = mask_value; p.out_idx = out_idx; p.out_val = out_val; p.dense = dense;
+  p.k = k; p.cap = cap; p.mask_value = mask_value; p.out_idx = out_idx; p.out_val = out_val; p.dense = dense;
   p.stages = 2;
   p.acc16 = acc16;
   {
     const char* dbg = getenv("LGCN_TC_DEBUG");
     p.debug_mode = dbg ? atoi(dbg) : 0;
   }
-  if (k <= 24) {
-    p.cap = 48;
-    return launch<D, TN, 2>(p, st);
+  return launch<D, TN, GROUPS, MT, NST>(p, st);
+}
+
+#define LGCN_TC_ARGS user_emb, item_emb, user_ids, n_eval, m_items, pos_rowptr, pos_sorted, k
+#define LGCN_TC_TAIL mask_value, out_idx, out_val, dense, workspace, workspace_bytes, acc16, st
+
+// Configuration choice.  TN1 = item-tile width of the one-user-tile layouts (256; 128 at d = 128).
+// Layout names (LGCN_TC_LAYOUT overrides the automatic choice for A-B runs); measured at
+// 75 776 users x 2 M items, d = 64, k = 20 (gpurun_out/tc*_sweep.log):
+//   m2g2  MT = 2 user tiles x TN = 128, one epilogue group per user tile, 6-deep operand ring
+//         (default for k <= 24, d <= 64, fp32 accumulators)                       605-610 TFLOP/s
+//   m2g4  the same with two column groups per user tile (16 epilogue warps, k <= 20)   545
+//   g2    one user tile x TN1, two column groups (the round-1 layout)                   494-505
+//   g4    one user tile x TN1, four column groups                                       443
+// Four TMEM accumulator stages (NST = 4: one user tile x TN 128, or two x TN 64) were slower
+// (433-444): the smaller tiles pay the per-tile hand-off more often.  24 < k <= 112: one group.
+template <int D, int TN1>
+static int run(const float* user_emb, const float* item_emb, const int64_t* user_ids, int n_eval,
+               int m_items, const int64_t* pos_rowptr, const int32_t* pos_sorted, int k,
+               float mask_value, int32_t* out_idx, float* out_val, float* dense, void* workspace,
+               size_t workspace_bytes, int acc16, cudaStream_t st) {
+  const char* le = getenv("LGCN_TC_LAYOUT");
+  const std::string layout = le ? le : "auto";
+  if constexpr (D <= 64) {
+    if (k <= 24 && !acc16) {
+      if (layout == "m2g2" || layout == "auto") return run_cfg<D, 128, 2, 2, 2>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
+    }
+    if (k <= 20 && !acc16 && layout == "m2g4") return run_cfg<D, 128, 4, 2, 2>(LGCN_TC_ARGS, 32, LGCN_TC_TAIL);
   }
+  if constexpr ((TN1 / 32) % 4 == 0) {
+    if (k <= 20 && layout == "g4" && !(acc16 && (TN1 / 64) % 4 != 0) && smem_need(D, TN1, 4, 1, 32) <= kSmemLimit)
+      return run_cfg<D, TN1, 4, 1, 2>(LGCN_TC_ARGS, 32, LGCN_TC_TAIL);
+  }
+  if (k <= 24) return run_cfg<D, TN1, 2, 1, 2>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
   int cap = 2 * k;
   if (cap < 64) cap = 64;
   if (cap > 128) cap = 128;
@@ -596,15 +730,17 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
     set_last_error("tensor-core top-k supports k <= 112 (got %d); use precision LGCN_F32", k);
     return LGCN_ERR_UNSUPPORTED;
   }
-  p.cap = cap;
-  return launch<D, TN, 1>(p, st);
+  return run_cfg<D, TN1, 1, 1, 2>(LGCN_TC_ARGS, cap, LGCN_TC_TAIL);
 }
+#undef LGCN_TC_ARGS
+#undef LGCN_TC_TAIL
 
 }  // namespace tc
 
 size_t score_topk_tc_workspace(int64_t n_eval, int64_t m_items, int d) {
+  // covers every layout: user tiles rounded up to a pair (MT = 2), item tiles at the widest TN
   const int tn = d >= 128 ? 128 : 256;
-  const int64_t n_ut = (n_eval + tc::kUM - 1) / tc::kUM, n_it = (m_items + tn - 1) / tn;
+  const int64_t n_ut = ((n_eval + 2 * tc::kUM - 1) / (2 * tc::kUM)) * 2, n_it = (m_items + tn - 1) / tn;
   return (size_t)n_ut * tc::kUM * d * 2 + (size_t)n_it * tn * d * 2;
 }
 
