@@ -342,9 +342,11 @@ score_topk_tc_kernel(const Params p) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int a = 0; a < NST; ++a) {
+    // one full/empty pair per (accumulator stage, user tile): the groups of a user tile hand their
+    // accumulator back without waiting for the other user tile's warps
+    for (int a = 0; a < NST * MT; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 128 * GROUPS);
+      mbar_init(bar_tempty + 8 * a, 128 * CG);
     }
     mbar_init(bar_afull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -383,12 +385,15 @@ score_topk_tc_kernel(const Params p) {
       mbar_wait(bar_afull, 0);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % S, a = j % NST;
-        if (j >= NST) mbar_wait(bar_tempty + 8 * a, ((j / NST) - 1) & 1);
         mbar_wait(bar_full + 8 * s, (j / S) & 1);
         tc_fence_after();
         const uint64_t bdesc0 = make_desc(smem_u32(sB + (size_t)s * kBBytes), TN * 16, 128);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
+          if (j >= NST) {
+            mbar_wait(bar_tempty + 8 * (a * MT + mt), ((j / NST) - 1) & 1);
+            tc_fence_after();
+          }
           const uint64_t adesc0 = make_desc(smem_u32(sA + (size_t)mt * kABytes), kUM * 16, 128);
 #pragma unroll
           for (int kk = 0; kk < kKSteps; ++kk) {
@@ -397,9 +402,9 @@ score_topk_tc_kernel(const Params p) {
             const uint64_t bd = bdesc0 + (uint64_t)((kk * 2 * TN * 16) >> 4);
             tc_mma_bf16(tmem_base + (a * MT + mt) * TN, ad, bd, kIdesc, kk > 0 ? 1u : 0u);
           }
+          tc_commit(bar_tfull + 8 * (a * MT + mt));   // this user tile's accumulator is ready for its groups
         }
         tc_commit(bar_empty + 8 * s);   // smem stage reusable once these MMAs retire
-        tc_commit(bar_tfull + 8 * a);   // accumulator stage ready for the epilogue
       }
     }
   } else if (warp >= kFrontWarps) {
@@ -433,28 +438,35 @@ score_topk_tc_kernel(const Params p) {
     // walk of the user's sorted train positives, in step with the item sweep
     int pp = 0;
     int next_pos = my_npos > 0 ? __ldg(my_pos) : 0x7fffffff;
-    // both epilogue groups work on every tile; group g owns the chunks [g*CPG, (g+1)*CPG).
-    // A chunk is one tcgen05.ld: 32 fp32 columns, or 64 packed f16 columns (ACC16).
-    constexpr int COLS = ACC16 ? 64 : 32;
+    // the column groups of a user tile split every item tile; group cg owns chunks [cg*CPG, (cg+1)*CPG).
+    // A chunk is 64 columns: two tcgen05.ld.x32 in flight (fp32), or one packed-f16 load (ACC16).
+    // Two independent max trees per trip halve the exposed latency chain (TMEM load -> tree ->
+    // vote -> branch) per score; with 2 epilogue warps per SM sub-partition that chain, not the
+    // TMEM bandwidth (tools/tmem_read_bw.cu), is what bounds the fast path.
+    constexpr int COLS = 64;
     constexpr int CPG = TN / COLS / CG;
     static_assert(CPG >= 1 && CPG * COLS * CG == TN, "every epilogue group needs whole chunks of the tile");
     const int c0 = cg * CPG;
 
     for (int j = 0; j < n_tiles; ++j) {
       const int a = j % NST;
-      mbar_wait(bar_tfull + 8 * a, (j / NST) & 1);
+      mbar_wait(bar_tfull + 8 * (a * MT + mt), (j / NST) & 1);
       tc_fence_after();
       const int item_tile0 = j * TN + c0 * COLS;
       const uint32_t tbase = tmem_base + lane_base + (uint32_t)((a * MT + mt) * TN + c0 * COLS);
 #pragma unroll 1
       for (int cc = 0; cc < (p.debug_mode == 1 ? 0 : CPG); ++cc) {
-        uint32_t r[32];
+        uint32_t r[32], r2[32];
         __syncwarp();
-        if (ACC16) tc_ld32_pack16(tbase + (uint32_t)(cc * COLS), r);
-        else tc_ld32(tbase + (uint32_t)(cc * COLS), r);
+        if (ACC16) {
+          tc_ld32_pack16(tbase + (uint32_t)(cc * COLS), r);
+        } else {
+          tc_ld32(tbase + (uint32_t)(cc * COLS), r);
+          tc_ld32(tbase + (uint32_t)(cc * COLS + 32), r2);
+        }
         tc_wait_ld();
         if (p.debug_mode == 2) {   // pipeline experiment: TMEM reads only, no selection work
-          if ((r[0] ^ r[31]) == 0x7fc12345u) sel.cnt = 1;
+          if ((r[0] ^ r[31] ^ (ACC16 ? 0u : r2[0] ^ r2[31])) == 0x7fc12345u) sel.cnt = 1;
           continue;
         }
         const int item0 = item_tile0 + cc * COLS;
@@ -467,33 +479,25 @@ score_topk_tc_kernel(const Params p) {
                 if (item0 + 2 * i + 1 < p.m_items) p.dense[grow * p.m_items + item0 + 2 * i + 1] = h2_hi(r[i]);
               } else {
                 if (item0 + i < p.m_items) p.dense[grow * p.m_items + item0 + i] = __uint_as_float(r[i]);
+                if (item0 + 32 + i < p.m_items) p.dense[grow * p.m_items + item0 + 32 + i] = __uint_as_float(r2[i]);
               }
             }
           }
         }
         if (!ACC16) {
-          // Fast path: one max tree per 32 scores against the row's threshold.  Slow path (some lane
-          // of the warp has a candidate): build the per-lane hit mask — after this r[] is dead, so
-          // nothing has to be kept alive across the candidate handling — then walk the columns any
-          // lane hit in ascending order, RE-READING that column from TMEM (a 1-register tcgen05.ld,
-          // ~40 clk; the accumulator stage is still ours) instead of indexing 32 live registers.
-          float m4[4];
-          const float cm = max32(r, m4);
-          if (__any_sync(0xffffffffu, cm > sel.thr)) {
-            // per-lane hit mask, built only for the 8-column blocks some lane of the warp hit
-            uint32_t hm = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              if (__any_sync(0xffffffffu, m4[b] > sel.thr)) {
-#pragma unroll
-                for (int i = 8 * b; i < 8 * b + 8; ++i) hm |= (__uint_as_float(r[i]) > sel.thr) ? (1u << i) : 0u;
-              }
-            }
-            uint32_t any = __reduce_or_sync(0xffffffffu, hm);
+          // Fast path: max trees of the two 32-column halves against the row's threshold, one vote.
+          // Slow path (some lane of the warp has a candidate), per half: build the per-lane hit mask —
+          // after this the registers are dead, so nothing has to be kept alive across the candidate
+          // handling — then walk the columns any lane hit in ascending order, RE-READING that column
+          // from TMEM (1-register tcgen05.ld; the accumulator stage is still ours) instead of
+          // indexing live registers.
+          float m4a[4], m4b[4];
+          const float cma = max32(r, m4a);
+          const float cmb = max32(r2, m4b);
+          if (__any_sync(0xffffffffu, fmaxf(cma, cmb) > sel.thr)) {
             // one candidate of this lane: positives walk, mask, append (ascending item ids)
-            auto take = [&](int c, uint32_t raw) {
+            auto take = [&](uint32_t hm, int c, int item, uint32_t raw) {
               if ((hm >> c) & 1u) {
-                const int item = item0 + c;
                 while (next_pos < item) {   // walk of the sorted train positives (ascending sweep)
                   ++pp;
                   next_pos = pp < my_npos ? __ldg(my_pos + pp) : 0x7fffffff;
@@ -509,19 +513,34 @@ score_topk_tc_kernel(const Params p) {
                 }
               }
             };
-            while (any) {   // two columns per round: both re-reads are in flight before the one wait
-              const int ca = __ffs(any) - 1;
-              any &= any - 1;
-              const bool two = any != 0;
-              const int cb = two ? __ffs(any) - 1 : ca;
-              any &= any - 1;   // no-op when any == 0
-              __syncwarp();     // the candidate handling below diverges; tcgen05.ld is warp-collective
-              const uint32_t ra = tc_ld1(tbase + (uint32_t)(cc * COLS + ca));
-              const uint32_t rb = tc_ld1(tbase + (uint32_t)(cc * COLS + cb));
-              tc_wait_ld();
-              take(ca, ra);
-              if (two) take(cb, rb);
-            }
+            auto slow_half = [&](const uint32_t(&rr)[32], const float(&m4)[4], float cm, int item_base, uint32_t tcol) {
+              if (!__any_sync(0xffffffffu, cm > sel.thr)) return;
+              // per-lane hit mask, built only for the 8-column blocks some lane of the warp hit
+              uint32_t hm = 0;
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                if (__any_sync(0xffffffffu, m4[b] > sel.thr)) {
+#pragma unroll
+                  for (int i = 8 * b; i < 8 * b + 8; ++i) hm |= (__uint_as_float(rr[i]) > sel.thr) ? (1u << i) : 0u;
+                }
+              }
+              uint32_t any = __reduce_or_sync(0xffffffffu, hm);
+              while (any) {   // two columns per round: both re-reads are in flight before the one wait
+                const int ca = __ffs(any) - 1;
+                any &= any - 1;
+                const bool two = any != 0;
+                const int cb = two ? __ffs(any) - 1 : ca;
+                any &= any - 1;   // no-op when any == 0
+                __syncwarp();     // the candidate handling below diverges; tcgen05.ld is warp-collective
+                const uint32_t ra = tc_ld1(tcol + (uint32_t)ca);
+                const uint32_t rb = tc_ld1(tcol + (uint32_t)cb);
+                tc_wait_ld();
+                take(hm, ca, item_base + ca, ra);
+                if (two) take(hm, cb, item_base + cb, rb);
+              }
+            };
+            slow_half(r, m4a, cma, item0, tbase + (uint32_t)(cc * COLS));
+            slow_half(r2, m4b, cmb, item0 + 32, tbase + (uint32_t)(cc * COLS + 32));
             if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
           }
         } else {
@@ -551,7 +570,7 @@ score_topk_tc_kernel(const Params p) {
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * a);
+      mbar_arrive(bar_tempty + 8 * (a * MT + mt));
     }
 
     sel = sel_compact(sel, mv, mi, NT, p.k);
@@ -718,8 +737,8 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
     }
     if (k <= 20 && !acc16 && layout == "m2g4") return run_cfg<D, 128, 4, 2, 2>(LGCN_TC_ARGS, 32, LGCN_TC_TAIL);
   }
-  if constexpr ((TN1 / 32) % 4 == 0) {
-    if (k <= 20 && layout == "g4" && !(acc16 && (TN1 / 64) % 4 != 0) && smem_need(D, TN1, 4, 1, 32) <= kSmemLimit)
+  if constexpr ((TN1 / 64) % 4 == 0) {
+    if (k <= 20 && layout == "g4" && smem_need(D, TN1, 4, 1, 32) <= kSmemLimit)
       return run_cfg<D, TN1, 4, 1, 2>(LGCN_TC_ARGS, 32, LGCN_TC_TAIL);
   }
   if (k <= 24) return run_cfg<D, TN1, 2, 1, 2>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
