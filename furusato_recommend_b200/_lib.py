@@ -66,6 +66,8 @@ SIGNATURES = {
     "lgcn_adam_tick": (C.c_int, [_P, _P, _D, _D, _D, _P]),
     "lgcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, _D, _D, _D, _P]),
     "lgcn_uniform_sample": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _I, C.c_uint64, C.c_uint32, _P, _P, _P]),
+    "lgcn_uniform_sample_weighted": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I, C.c_uint64, C.c_uint32,
+                                               _P, _P, _P]),
     "lgcn_compact_triples": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
     "lgcn_score_topk": (C.c_int, [_P, _P, _P, _I64, _I64, _I, _P, _P, _I, _F, _I, _P, _P, _P, _I64, _P]),
     "lgcn_score_topk_workspace_bytes": (C.c_int64, [_I64, _I64, _I, _I]),

@@ -36,9 +36,24 @@ __device__ __forceinline__ bool contains_sorted(const int32_t* __restrict__ a, i
   return lo < n && __ldg(a + lo) == x;
 }
 
+// Weighted positive pick (negative_sample.py:53-56, np.random.choice(len(pos), p=probs[user])):
+// numpy draws one uniform u and returns searchsorted(cumsum(p) / sum, u, side='right').  Here
+// u = (r >> 8) * 2^-24 from the sample's second Philox word and cdf is the user's inclusive,
+// normalised fp32 cumulative table: the first j with cdf[j] > u (clamped to the last entry).
+__device__ __forceinline__ int64_t pick_by_cdf(const float* __restrict__ cdf, int64_t n, uint32_t r) {
+  const float u = (float)(r >> 8) * 5.9604644775390625e-08f;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(cdf + mid) > u) hi = mid; else lo = mid + 1;
+  }
+  return lo < n ? lo : n - 1;
+}
+
 __global__ void __launch_bounds__(256)
 uniform_sample_kernel(const int64_t* __restrict__ pos_rowptr, const int32_t* __restrict__ pos_file,
-                      const int32_t* __restrict__ pos_sorted, uint32_t n_users, uint32_t m_items,
+                      const int32_t* __restrict__ pos_sorted, const float* __restrict__ pos_cdf,
+                      uint32_t n_users, uint32_t m_items,
                       int64_t first, int64_t count, int n_neg, uint32_t seed_lo, uint32_t seed_hi,
                       uint32_t epoch, int64_t* __restrict__ triples, uint8_t* __restrict__ valid) {
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,7 +73,8 @@ uniform_sample_kernel(const int64_t* __restrict__ pos_rowptr, const int32_t* __r
     }
     return;
   }
-  const int64_t positem = pos_file[b + __umulhi(r[1], (uint32_t)len)];
+  const int64_t positem = pos_cdf != nullptr ? pos_file[b + pick_by_cdf(pos_cdf + b, len, r[1])]
+                                             : pos_file[b + __umulhi(r[1], (uint32_t)len)];
   uint32_t j = 2, blk = 0;
   for (int t = 0; t < n_neg; ++t) {   // n_neg > 1: the sampled-softmax layout, flat (u, pos, neg_t) rows
     int32_t negitem;
@@ -171,11 +187,26 @@ tile_scatter_kernel(const int64_t* __restrict__ triples, const uint8_t* __restri
 
 using namespace lgcn;
 
+extern "C" int lgcn_uniform_sample_weighted(const int64_t* pos_rowptr, const int32_t* pos_file,
+                                            const int32_t* pos_sorted, const float* pos_cdf, int64_t n_users,
+                                            int64_t m_items, int64_t first, int64_t count, int n_neg,
+                                            uint64_t seed, uint32_t epoch, int64_t* triples, uint8_t* valid,
+                                            lgcn_stream_t stream);
+
 extern "C" int lgcn_uniform_sample(const int64_t* pos_rowptr, const int32_t* pos_file,
                                    const int32_t* pos_sorted, int64_t n_users, int64_t m_items,
                                    int64_t first, int64_t count, int n_neg, uint64_t seed,
                                    uint32_t epoch, int64_t* triples, uint8_t* valid,
                                    lgcn_stream_t stream) {
+  return lgcn_uniform_sample_weighted(pos_rowptr, pos_file, pos_sorted, nullptr, n_users, m_items, first, count,
+                                      n_neg, seed, epoch, triples, valid, stream);
+}
+
+extern "C" int lgcn_uniform_sample_weighted(const int64_t* pos_rowptr, const int32_t* pos_file,
+                                            const int32_t* pos_sorted, const float* pos_cdf, int64_t n_users,
+                                            int64_t m_items, int64_t first, int64_t count, int n_neg,
+                                            uint64_t seed, uint32_t epoch, int64_t* triples, uint8_t* valid,
+                                            lgcn_stream_t stream) {
   LGCN_CHECK_ARG(pos_rowptr && pos_file && pos_sorted && triples && valid, "null pointer argument");
   LGCN_CHECK_ARG(n_users > 0 && n_users < 0xffffffffLL, "n_users out of range");
   LGCN_CHECK_ARG(m_items > 0 && m_items < 0x7fffffffLL, "m_items out of range");
@@ -185,7 +216,7 @@ extern "C" int lgcn_uniform_sample(const int64_t* pos_rowptr, const int32_t* pos
   const int64_t blocks = (count + 255) / 256;
   LGCN_CHECK_ARG(blocks < 0x7fffffffLL, "count too large");
   uniform_sample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      pos_rowptr, pos_file, pos_sorted, (uint32_t)n_users, (uint32_t)m_items, first, count, n_neg,
+      pos_rowptr, pos_file, pos_sorted, pos_cdf, (uint32_t)n_users, (uint32_t)m_items, first, count, n_neg,
       (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), epoch, triples, valid);
   LGCN_LAUNCH_OK();
   return 0;

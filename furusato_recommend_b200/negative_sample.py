@@ -79,3 +79,61 @@ def UniformSampleCapped(dataset, neg_ratio: int = 1, *, limit: int = POSITIVE_NU
     keep = torch.zeros(count, dtype=torch.uint8, device=key.device)
     keep[order] = keep_sorted.to(torch.uint8)
     return ops.compact_triples(triples, keep)
+
+
+class UniformSampling:
+    """`UniformSampling(dataset, config).sample()` of the reference (negative_sample.py:12-96): the
+    multi-process sampler whose positive is drawn by popularity-powered probabilities when
+    `config['sample_pow'] != 0` (`np.random.choice(len(pos), p=self.probs[user])`, :53-56).
+
+    The reference unpickles `self.probs` from `./data/sample_prob/sample_prob_XX.pkl` (private
+    files); here `probs` is passed in — a sequence of per-user arrays aligned with `allPos[u]`
+    (file order) or one flat array in that order.  When omitted, p_j ∝ popularity(item_j)^(-sample_pow)
+    is used (our reading of the file names; say so if you rely on it).  `sample_pow == 0` is the
+    uniform pick (:51-52).  The four forked workers of the reference all inherit the same numpy RNG
+    state and drop the remainder of count / 4 (:41-42); with per-sample Philox streams there is
+    nothing to fork: one launch draws `trainDataSize` samples."""
+
+    def __init__(self, dataset, config, neg_ratio: int = 1, probs=None):
+        self.dataset, self.config = dataset, config
+        self.sample_pow = float(config.get("sample_pow", 0))
+        self.m_items, self.n_users, self.user_num = dataset.m_items, dataset.n_user, dataset.trainDataSize
+        self._cdf = None
+        if self.sample_pow != 0:
+            rowptr, file_items, _ = dataset.pos_csr()
+            dev = rowptr.device
+            if probs is None:
+                pop = torch.bincount(file_items.long(), minlength=self.m_items).to(torch.float64)
+                w = pop[file_items.long()].pow(-self.sample_pow)
+            elif torch.is_tensor(probs):
+                w = probs.to(device=dev, dtype=torch.float64).flatten()
+            else:
+                import numpy as np
+                flat = probs if isinstance(probs, np.ndarray) and probs.ndim == 1 else np.concatenate([np.asarray(p) for p in probs])
+                w = torch.as_tensor(flat, dtype=torch.float64, device=dev)
+            if w.numel() != file_items.numel():
+                raise ValueError("probs must align with the train interactions (allPos order)")
+            self._cdf = _segment_cdf(w, rowptr)
+
+    def sample(self, *, seed: int | None = None, epoch: int | None = None, count: int | None = None) -> torch.Tensor:
+        if epoch is None:
+            epoch = _STATE["epoch"]
+            _STATE["epoch"] += 1
+        if seed is None:
+            seed = _STATE["seed"]
+        rowptr, file_items, sorted_items = self.dataset.pos_csr()
+        triples, valid = ops.uniform_sample(rowptr, file_items, sorted_items, self.n_users, self.m_items,
+                                            self.user_num if count is None else count, seed, epoch, pos_cdf=self._cdf)
+        return ops.compact_triples(triples, valid)
+
+
+def _segment_cdf(w: torch.Tensor, rowptr: torch.Tensor) -> torch.Tensor:
+    """Per-user inclusive cumulative sums of w, normalised to end at 1 (numpy: cdf = p.cumsum();
+    cdf /= cdf[-1]), in float64, stored as fp32."""
+    c = torch.cumsum(w, 0)
+    lens = rowptr[1:] - rowptr[:-1]
+    start = torch.cat([torch.zeros(1, dtype=c.dtype, device=c.device), c])[rowptr[:-1]]   # sum before each user
+    seg = torch.repeat_interleave(torch.arange(lens.numel(), device=c.device), lens)
+    local = c - start[seg]
+    total = torch.zeros(lens.numel(), dtype=c.dtype, device=c.device).index_add_(0, seg, w)
+    return (local / total[seg]).to(torch.float32).contiguous()

@@ -152,17 +152,22 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch
 
 def uniform_sample(pos_rowptr: torch.Tensor, pos_file: torch.Tensor, pos_sorted: torch.Tensor,
                    n_users: int, m_items: int, count: int, seed: int, epoch: int, first: int = 0,
-                   n_neg: int = 1):
-    """Returns (triples int64[count,3], valid uint8[count]) — not yet compacted."""
+                   n_neg: int = 1, pos_cdf: Optional[torch.Tensor] = None):
+    """Returns (triples int64[count,3], valid uint8[count]) — not yet compacted.  `pos_cdf` (fp32,
+    aligned with pos_file: per-user normalised inclusive cumulative probabilities) switches the
+    positive pick from uniform to weighted (lgcn_uniform_sample_weighted)."""
     lib = _lib.load()
     dev = pos_rowptr.device
     triples = torch.empty((count * n_neg, 3), dtype=torch.int64, device=dev)
     valid = torch.empty(count * n_neg, dtype=torch.uint8, device=dev)
-    _lib.check(lib.lgcn_uniform_sample(
+    if pos_cdf is not None and pos_cdf.numel() != pos_file.numel():
+        raise ValueError("pos_cdf must align with pos_file")
+    _lib.check(lib.lgcn_uniform_sample_weighted(
         _chk(pos_rowptr, torch.int64, "pos_rowptr"), _chk(pos_file, torch.int32, "pos_file"),
-        _chk(pos_sorted, torch.int32, "pos_sorted"), n_users, m_items, first, count, n_neg,
+        _chk(pos_sorted, torch.int32, "pos_sorted"), _chk(pos_cdf, torch.float32, "pos_cdf", True),
+        n_users, m_items, first, count, n_neg,
         seed & 0xFFFFFFFFFFFFFFFF, epoch & 0xFFFFFFFF, triples.data_ptr(), valid.data_ptr(), _stream()),
-        "lgcn_uniform_sample")
+        "lgcn_uniform_sample_weighted")
     return triples, valid
 
 

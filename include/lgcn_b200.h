@@ -199,6 +199,17 @@ int lgcn_uniform_sample(const int64_t* pos_rowptr, const int32_t* pos_file, cons
                         int n_neg, uint64_t seed, uint32_t epoch, int64_t* triples,
                         uint8_t* valid, lgcn_stream_t stream);
 
+/* Same sampler with a weighted positive pick — UniformSampling.sample_parallel with
+ * config['sample_pow'] != 0 (negative_sample.py:53-56: np.random.choice(len(pos), p=probs[user])).
+ * pos_cdf: fp32[nnz_pos], aligned with pos_file: per user the inclusive cumulative sum of its
+ * probabilities, normalised so the last entry is 1.  The pick is the first j with cdf[j] > u,
+ * u = (word >> 8) * 2^-24 of the sample's second Philox word (numpy: searchsorted(cdf, u, 'right')).
+ * pos_cdf == NULL is lgcn_uniform_sample. */
+int lgcn_uniform_sample_weighted(const int64_t* pos_rowptr, const int32_t* pos_file, const int32_t* pos_sorted,
+                                 const float* pos_cdf, int64_t n_users, int64_t m_items, int64_t first,
+                                 int64_t count, int n_neg, uint64_t seed, uint32_t epoch, int64_t* triples,
+                                 uint8_t* valid, lgcn_stream_t stream);
+
 /* Order-preserving compaction of the valid triples (np.array(S), :134).
  * scratch: int64[ceil(count/1024) + 1]; n_out: device int64[1]. */
 int lgcn_compact_triples(const int64_t* triples, const uint8_t* valid, int64_t count,

@@ -214,21 +214,23 @@ def sparse_graph_full(graph):
 # 9.4 sampler  (negative_sample.py:98-134)
 # --------------------------------------------------------------------------
 def uniform_sample_core(all_pos: Sequence[np.ndarray], sample_users: np.ndarray,
-                        next_int: Callable[[int, int], int], n_neg: int = 1) -> np.ndarray:
+                        next_int: Callable[[int, int], int], n_neg: int = 1,
+                        pos_index: Callable[[int, int, int], int] = None) -> np.ndarray:
     """The reference's per-sample decision procedure, RNG factored out.
 
     negative_sample.py:113-130: for each drawn user IN ORDER: empty positive
     list -> emit nothing (:116-117); positive = allPos[user][randint(len)] in
     FILE ORDER, duplicates weigh the draw (:119-120); negative = first
     randint(m_items) whose value is not contained in allPos[user] (:121-126).
-    `next_int(i, k)` returns the next draw in [0,k) for sample i.
+    `next_int(i, k)` returns the next draw in [0,k) for sample i.  `pos_index(i, user, len)`
+    replaces the uniform positive pick (negative_sample.py:53-56, weighted by probs[user]).
     """
     S = []
     for i, user in enumerate(sample_users):
         P = all_pos[int(user)]
         if len(P) == 0:
             continue
-        positem = P[next_int(i, len(P))]
+        positem = P[next_int(i, len(P)) if pos_index is None else pos_index(i, int(user), len(P))]
         for _ in range(n_neg):  # n_neg > 1: flat (u, pos, neg_t) rows, the lgcnssm.py:141 batch layout
             while True:
                 neg = next_int(i, -1)
@@ -288,7 +290,8 @@ def philox_randint(r: int, k: int) -> int:
 
 
 def uniform_sample_philox(all_pos: Sequence[np.ndarray], n_users: int, m_items: int,
-                          count: int, seed: int, epoch: int, n_neg: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+                          count: int, seed: int, epoch: int, n_neg: int = 1,
+                          pos_cdf: Sequence[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
     """Sampler with the "same uniform draws" contract of SURVEY §9.4.
 
     Draw j of sample i is word (j % 4) of Philox4x32-10(key=(seed_lo, seed_hi),
@@ -323,8 +326,15 @@ def uniform_sample_philox(all_pos: Sequence[np.ndarray], n_users: int, m_items: 
     def next_int(i, k):
         return philox_randint(draw(i), m_items if k < 0 else k)
 
+    def pos_index(i, user, n):
+        # weighted pick (our spec of np.random.choice's inverse-CDF step): u = (word >> 8) * 2^-24 as
+        # fp32, first j with cdf[j] > u, clamped; pos_cdf[user] is the fp32 normalised cumulative table
+        u = np.float32((draw(i) >> 8) * 5.9604644775390625e-08)
+        j = int(np.searchsorted(pos_cdf[user], u, side="right"))
+        return min(j, n - 1)
+
     valid = np.array([len(all_pos[int(u)]) > 0 for u in sample_users], dtype=bool)
-    S = uniform_sample_core(all_pos, sample_users, next_int, n_neg)
+    S = uniform_sample_core(all_pos, sample_users, next_int, n_neg, pos_index if pos_cdf is not None else None)
     return S, valid
 
 
@@ -543,3 +553,24 @@ def capped_sample_philox(all_pos, n_users: int, m_items: int, count: int, seed: 
         else:
             oc[p] = c + 1
     return S[keep]
+
+
+def weighted_sample_mt(all_pos, probs, n_users: int, m_items: int, count: int) -> np.ndarray:
+    """`UniformSampling.sample` / `sample_parallel` with `sample_pow != 0` under the reference's RNG
+    (negative_sample.py:39-69,73-74): users from one vectorised randint, positive index by
+    np.random.choice(len(pos), p=probs[user]) (:56), negatives by rejection."""
+    sample_users = np.random.randint(0, n_users, count)
+
+    def next_int(_i, k):
+        return np.random.randint(0, m_items if k < 0 else k)
+
+    def pos_index(_i, user, n):
+        return int(np.random.choice(n, p=probs[user]))
+
+    return uniform_sample_core(all_pos, sample_users, next_int, 1, pos_index)
+
+
+def normalised_cdf(p: np.ndarray) -> np.ndarray:
+    """np.random.choice's table: cdf = p.cumsum(); cdf /= cdf[-1] (float64), stored as fp32."""
+    c = np.cumsum(np.asarray(p, dtype=np.float64))
+    return (c / c[-1]).astype(np.float32)

@@ -160,6 +160,31 @@ def main():
     out["capped_philox_seed9_epoch1"] = orc.capped_sample_philox(ds.allPos, n, m, 3000, seed=9, epoch=1, limit=CAP)
     print(f"[capped sampler] {len(S_ref)} of {ds.trainDataSize * 3} triples kept, identical under MT19937 seed 321")
 
+    # popularity-weighted positive pick of UniformSampling (negative_sample.py:12-69): the class
+    # unpickles per-user probabilities from a fixed relative path (:22-36); feed it ours.
+    import pickle
+    import negative_sample as ref_ns
+    pop = np.bincount(ds.trainItem, minlength=m).astype(np.float64)
+    probs = [(pop[p] ** -0.5) / (pop[p] ** -0.5).sum() if len(p) else np.zeros(0) for p in ds.allPos]
+    (tmp / "data" / "sample_prob").mkdir(parents=True)
+    with open(tmp / "data" / "sample_prob" / "sample_prob_05.pkl", "wb") as f:
+        pickle.dump(probs, f)
+    ds.n_user = n
+    ref_ns.tqdm = lambda it, *a, **k: it
+    sampler = ref_ns.UniformSampling(ds, {"sample_pow": 0.5})
+    np.random.seed(77)
+    users_drawn = np.random.randint(0, n, 4000)
+    ret = {}
+    sampler.sample_parallel(0, 1, users_drawn, ds.allPos, ret)
+    np.random.seed(77)
+    W_orc = orc.weighted_sample_mt(ds.allPos, probs, n, m, 4000)
+    assert np.array_equal(ret[0], W_orc), "weighted sampler decision procedure differs"
+    cdfs = [orc.normalised_cdf(p) if len(p) else np.zeros(0, np.float32) for p in probs]
+    out["weighted_mt_seed77"] = ret[0]
+    out["weighted_probs_flat"] = np.concatenate(probs)
+    out["weighted_philox_seed4_epoch2"] = orc.uniform_sample_philox(ds.allPos, n, m, 3000, seed=4, epoch=2, pos_cdf=cdfs)[0]
+    print(f"[weighted sampler] {len(W_orc)} triples identical under MT19937 seed 77 (sample_pow=0.5)")
+
     np.savez_compressed(GOLD / "variants_ref.npz", **out)
     print("wrote", GOLD / "variants_ref.npz", f"{(GOLD / 'variants_ref.npz').stat().st_size / 1024:.0f} KiB")
 

@@ -100,3 +100,30 @@ def test_capped_sampler_bit_exact(golden, variants):
     train = [ds.allPos[u] for u in range(ds.n_users)]
     full, _ = orc.uniform_sample_philox(train, ds.n_users, ds.m_items, 3 * ds.trainDataSize, seed=9, epoch=1)
     assert np.array_equal(big.cpu().numpy(), full)
+
+
+def test_weighted_positive_sampler_bit_exact(golden, variants):
+    from furusato_recommend_b200 import UniformSampling
+    ds = golden_dataset(golden)
+    flat = variants["weighted_probs_flat"]
+    s = UniformSampling(ds, {"sample_pow": 0.5}, probs=flat)
+    S = s.sample(seed=4, epoch=2, count=3000)
+    # the device inverse-CDF table against numpy's per-user cumsum (np.random.choice's table)
+    train = [ds.allPos[u] for u in range(ds.n_users)]
+    ptr = np.concatenate([[0], np.cumsum([len(p) for p in train])])
+    cdf_dev = s._cdf.cpu().numpy()
+    cdfs = [cdf_dev[ptr[u]:ptr[u + 1]] for u in range(ds.n_users)]
+    want = np.concatenate([orc.normalised_cdf(flat[ptr[u]:ptr[u + 1]]) for u in range(ds.n_users) if ptr[u + 1] > ptr[u]])
+    assert np.abs(cdf_dev - want).max() < 1e-6
+    # the kernel's decision procedure, bit-exact on its own table
+    P, _ = orc.uniform_sample_philox(train, ds.n_users, ds.m_items, 3000, seed=4, epoch=2, pos_cdf=cdfs)
+    assert np.array_equal(S.cpu().numpy(), P)
+    if np.array_equal(cdf_dev, want):   # identical tables -> identical to the frozen vector
+        assert np.array_equal(S.cpu().numpy(), variants["weighted_philox_seed4_epoch2"])
+    # default probabilities: popularity^-pow, and sample_pow = 0 is the plain uniform sampler
+    d = UniformSampling(ds, {"sample_pow": 0.5}).sample(seed=4, epoch=2, count=3000)
+    pop = np.bincount(golden["train_item"], minlength=ds.m_items)
+    u0 = UniformSampling(ds, {"sample_pow": 0}).sample(seed=4, epoch=2, count=3000)
+    full, _ = orc.uniform_sample_philox(train, ds.n_users, ds.m_items, 3000, seed=4, epoch=2)
+    assert np.array_equal(u0.cpu().numpy(), full)
+    assert pop[d[:, 1].cpu().numpy()].mean() < pop[full[:, 1]].mean()

@@ -90,3 +90,25 @@ def test_capped_sampler(golden, variants, tiny_lists):
     full, _ = orc.uniform_sample_philox(train, n, m, 3000, seed=9, epoch=1)
     it = iter(full.tolist())
     assert all(any(row == cand for cand in it) for row in P.tolist())
+
+
+def test_weighted_positive_sampler(golden, variants, tiny_lists):
+    """UniformSampling with sample_pow != 0 (negative_sample.py:53-56): decision procedure under the
+    reference's RNG, and the Philox restatement on fp32 inverse-CDF tables."""
+    train, _ = tiny_lists
+    n, m = int(golden["n_users"]), int(golden["m_items"])
+    flat = variants["weighted_probs_flat"]
+    ptr = np.concatenate([[0], np.cumsum([len(p) for p in train])])
+    probs = [flat[ptr[u]:ptr[u + 1]] for u in range(n)]
+    np.random.seed(77)
+    W = orc.weighted_sample_mt(train, probs, n, m, 4000)
+    assert np.array_equal(W, variants["weighted_mt_seed77"])
+    cdfs = [orc.normalised_cdf(p) if len(p) else np.zeros(0, np.float32) for p in probs]
+    P, _ = orc.uniform_sample_philox(train, n, m, 3000, seed=4, epoch=2, pos_cdf=cdfs)
+    assert np.array_equal(P, variants["weighted_philox_seed4_epoch2"])
+    # same users and negatives' acceptance rule as the uniform sampler; only the positive pick moves
+    U, _ = orc.uniform_sample_philox(train, n, m, 3000, seed=4, epoch=2)
+    assert np.array_equal(P[:, 0], U[:, 0]) and not np.array_equal(P[:, 1], U[:, 1])
+    # rare items are preferred: mean popularity of the weighted positives is lower
+    pop = np.bincount(golden["train_item"], minlength=m)
+    assert pop[P[:, 1]].mean() < pop[U[:, 1]].mean()
