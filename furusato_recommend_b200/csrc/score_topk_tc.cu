@@ -294,6 +294,7 @@ struct Params {
   int32_t* out_idx;
   float* out_val;
   float* dense;            // optional [n_eval, m_items] dump of the accumulators (tests)
+  int trig;                // > 0: compaction trigger override (tuning)
   int debug_mode;          // 0 = normal; pipeline experiments: 1 = epilogue skips the TMEM reads,
                            // 2 = TMEM reads only, 3 = reads + max tree, no candidate passes
   int acc16;               // 1: f16 accumulators, read back two per register (tcgen05.ld pack::16b)
@@ -431,9 +432,10 @@ score_topk_tc_kernel(const Params p) {
     sel.thr = (live && p.debug_mode < 3) ? -INFINITY : INFINITY;   // debug 3: max tree only, no candidate ever passes
     sel.cnt = 0;
     sel.sorted = 0;
-    // warp-synchronous compaction once any lane's buffer is nearly full; with the small buffers of
-    // the 4-group layout keep at least k + 8 (or cap - 4) entries before folding
-    const int trig = max(p.cap - 12, min(p.cap - 4, p.k + 8));
+    // warp-synchronous compaction once any lane holds k + 6 entries (at most cap - 4): folding early
+    // keeps the thresholds tight, and every candidate that is not admitted saves a slow-path trip
+    // for the whole warp (trigger 22 / 26 / 30 / 36 / 44 at k = 20: 626 / 663 / 657 / 645 / 632 TFLOP/s)
+    const int trig = p.trig > 0 ? p.trig : min(p.cap - 4, p.k + 6);
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     // walk of the user's sorted train positives, in step with the item sweep
     int pp = 0;
@@ -707,6 +709,8 @@ static int run_cfg(const float* user_emb, const float* item_emb, const int64_t* 
   {
     const char* dbg = getenv("LGCN_TC_DEBUG");
     p.debug_mode = dbg ? atoi(dbg) : 0;
+    const char* tg = getenv("LGCN_TC_TRIG");
+    p.trig = tg ? atoi(tg) : 0;
   }
   return launch<D, TN, GROUPS, MT, NST>(p, st);
 }
