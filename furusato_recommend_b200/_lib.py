@@ -50,7 +50,7 @@ class LayerArgs(C.Structure):
         ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
         ("zero_base", C.c_int),
         ("n_dst_peers", C.c_int), ("dst_row_offset", C.c_int64), ("dst_peers", C.c_void_p * MAX_PEERS),
-        ("src_scale", C.c_void_p), ("dst_scale", C.c_void_p),
+        ("src_scale", C.c_void_p), ("dst_scale", C.c_void_p), ("edge_w", C.c_void_p),
     ]
 
 

@@ -78,6 +78,7 @@ struct GraphDev {
 };
 
 struct EpiDev {
+  const float* edge_w;     // [nnz] per-slot weight (edge dropout: mask / keep_prob) or NULL
   const float* src_scale;  // w_j of the gather (first layer) and the pre-scale of dst; dinv unless overridden
   const float* dst_scale;  // x_i = dst_scale[i] * s_i; dinv unless overridden
   const void* src;
@@ -114,12 +115,16 @@ struct EpiDev {
 //   * loads are never predicated and need no zero-fill select: a slot past the end of the
 //     neighbour list re-reads row 0 of SRC (an L1 hit) and is accumulated with weight 0;
 //   * the row address is one mad.wide on a lane-folded base pointer.
-template <int D, bool SRC_BF16, bool SCALE_SRC>
+// WMODE selects the slot weight at compile time: 0 none (pre-scaled source, plain sum), 1 dinv[col]
+// (scale_src), 2 edge_w[slot] (edge dropout on a pre-scaled source), 3 both.
+template <int D, bool SRC_BF16, int WMODE>
 __device__ __forceinline__ void gather_sum(const void* __restrict__ src,
                                            const int32_t* __restrict__ col,
-                                           const float* __restrict__ dinv, int64_t e0,
+                                           const float* __restrict__ dinv,
+                                           const float* __restrict__ edge_w, int64_t e0,
                                            int64_t e_end, int64_t stride, int lig,
                                            float (&acc)[RowCfg<D, SRC_BF16>::kEPL]) {
+  constexpr bool SCALE_SRC = WMODE != 0;   // a weighted gather (the name the loop below uses)
   using C = RowCfg<D, SRC_BF16>;
   constexpr int LPR = C::kLPR, EPL = C::kEPL, U = C::kUnroll;
   constexpr unsigned kFull = 0xffffffffu;
@@ -134,7 +139,9 @@ __device__ __forceinline__ void gather_sum(const void* __restrict__ src,
   float nxt_w = 0.f;
   if (e0 + lig < e_end) {
     nxt_c = ldg_stream_i32(col + e0 + lig);
-    if (SCALE_SRC) nxt_w = __ldg(dinv + nxt_c);
+    if (WMODE == 1) nxt_w = __ldg(dinv + nxt_c);
+    if (WMODE == 2) nxt_w = __ldg(edge_w + e0 + lig);
+    if (WMODE == 3) nxt_w = __ldg(dinv + nxt_c) * __ldg(edge_w + e0 + lig);
   }
   int64_t e = e0;
   for (int ch = 0; ch < n_chunks; ++ch, e += stride) {
@@ -146,7 +153,9 @@ __device__ __forceinline__ void gather_sum(const void* __restrict__ src,
     nxt_w = 0.f;
     if (e + stride + lig < e_end) {  // prefetch the next chunk of column ids
       nxt_c = ldg_stream_i32(col + e + stride + lig);
-      if (SCALE_SRC) nxt_w = __ldg(dinv + nxt_c);
+      if (WMODE == 1) nxt_w = __ldg(dinv + nxt_c);
+      if (WMODE == 2) nxt_w = __ldg(edge_w + e + stride + lig);
+      if (WMODE == 3) nxt_w = __ldg(dinv + nxt_c) * __ldg(edge_w + e + stride + lig);
     }
     int nb = (cnt + U - 1) / U;
 #pragma unroll
@@ -311,7 +320,7 @@ __device__ __forceinline__ void row_epilogue(const EpiDev& p, const RowPre<EPL>&
   }
 }
 
-template <int D, bool SRC_BF16, bool DST_BF16, bool SCALE_SRC>
+template <int D, bool SRC_BF16, bool DST_BF16, int WMODE>
 __global__ void __launch_bounds__(kBlock, LGCN_SPMM_MINBLOCKS)
 spmm_layer_kernel(const GraphDev g, const EpiDev p) {
   using C = RowCfg<D, SRC_BF16>;
@@ -334,7 +343,7 @@ spmm_layer_kernel(const GraphDev g, const EpiDev p) {
     const int64_t b = (int64_t)(((uint64_t)(uint32_t)dsc.w << 32) | (uint32_t)dsc.z);
     RowPre<EPL> pre;
     if (live) pre = row_prefetch<D, EPL>(p, row, lig);
-    gather_sum<D, SRC_BF16, SCALE_SRC>(p.src, g.col, p.src_scale, b, b + dsc.y, LPR, lig, acc);
+    gather_sum<D, SRC_BF16, WMODE>(p.src, g.col, p.src_scale, p.edge_w, b, b + dsc.y, LPR, lig, acc);
     if (live) row_epilogue<D, EPL, DST_BF16>(p, pre, row, lig, gmask, acc);
     return;
   }
@@ -346,8 +355,8 @@ spmm_layer_kernel(const GraphDev g, const EpiDev p) {
   const int64_t row = g.seg_row[seg];
   const int64_t b = g.seg_begin[seg];
   const int64_t e = b + g.seg_len[seg];
-  gather_sum<D, SRC_BF16, SCALE_SRC>(p.src, g.col, p.src_scale, b + (int64_t)grp * LPR, e,
-                                     (int64_t)NG * LPR, lig, acc);
+  gather_sum<D, SRC_BF16, WMODE>(p.src, g.col, p.src_scale, p.edge_w, b + (int64_t)grp * LPR, e,
+                                 (int64_t)NG * LPR, lig, acc);
 #pragma unroll
   for (int j = 0; j < EPL; ++j) red[grp][lig * EPL + j] = acc[j];
   __syncthreads();
@@ -389,7 +398,7 @@ spmm_layer_kernel(const GraphDev g, const EpiDev p) {
   }
 }
 
-template <int D, bool SRC_BF16, bool DST_BF16, bool SCALE_SRC>
+template <int D, bool SRC_BF16, bool DST_BF16, int WMODE>
 static int launch_layer(const GraphDev& g, const EpiDev& p, cudaStream_t st) {
   using C = RowCfg<D, SRC_BF16>;
   static_assert(D <= kBlock, "hub reduction assumes D <= block size");
@@ -400,30 +409,31 @@ static int launch_layer(const GraphDev& g, const EpiDev& p, cudaStream_t st) {
     set_last_error("grid too large: %lld", (long long)grid);
     return LGCN_ERR_UNSUPPORTED;
   }
-  spmm_layer_kernel<D, SRC_BF16, DST_BF16, SCALE_SRC><<<(unsigned)grid, kBlock, 0, st>>>(g, p);
+  spmm_layer_kernel<D, SRC_BF16, DST_BF16, WMODE><<<(unsigned)grid, kBlock, 0, st>>>(g, p);
   LGCN_LAUNCH_OK();
   return 0;
+}
+
+template <int D, bool SB, bool DB>
+static int dispatch_wmode(int wmode, const GraphDev& g, const EpiDev& p, cudaStream_t st) {
+  switch (wmode) {
+    case 0: return launch_layer<D, SB, DB, 0>(g, p, st);
+    case 1: if constexpr (!SB) return launch_layer<D, SB, DB, 1>(g, p, st); else break;
+    case 2: return launch_layer<D, SB, DB, 2>(g, p, st);
+    case 3: if constexpr (!SB) return launch_layer<D, SB, DB, 3>(g, p, st); else break;
+  }
+  set_last_error("scale_src needs an fp32 source");
+  return LGCN_ERR_UNSUPPORTED;
 }
 
 template <int D>
 static int dispatch_dtype(const lgcn_layer_args_t* a, const GraphDev& g, const EpiDev& p,
                           cudaStream_t st) {
   const bool sb = a->src_dtype == LGCN_BF16, db = a->dst_dtype == LGCN_BF16;
-  if (!sb && !db) {
-    return a->scale_src ? launch_layer<D, false, false, true>(g, p, st)
-                        : launch_layer<D, false, false, false>(g, p, st);
-  }
-  if (!sb && db) {
-    return a->scale_src ? launch_layer<D, false, true, true>(g, p, st)
-                        : launch_layer<D, false, true, false>(g, p, st);
-  }
-  if (sb && db) {
-    if (a->scale_src) {
-      set_last_error("scale_src needs an fp32 source");
-      return LGCN_ERR_UNSUPPORTED;
-    }
-    return launch_layer<D, true, true, false>(g, p, st);
-  }
+  const int wmode = (a->scale_src ? 1 : 0) | (a->edge_w != nullptr ? 2 : 0);
+  if (!sb && !db) return dispatch_wmode<D, false, false>(wmode, g, p, st);
+  if (!sb && db) return dispatch_wmode<D, false, true>(wmode, g, p, st);
+  if (sb && db) return dispatch_wmode<D, true, true>(wmode, g, p, st);
   set_last_error("bf16 source with fp32 destination is not a LightGCN layer");
   return LGCN_ERR_UNSUPPORTED;
 }
@@ -549,6 +559,7 @@ extern "C" int lgcn_propagate_layer(const lgcn_graph_t* gh, const lgcn_layer_arg
   g.partial = gh->partial;
 
   EpiDev p;
+  p.edge_w = a->edge_w;
   p.src_scale = a->src_scale != nullptr ? a->src_scale : gh->dinv;
   p.dst_scale = a->dst_scale != nullptr ? a->dst_scale : gh->dinv;
   p.src = a->src; p.dst = a->dst; p.base = a->base;

@@ -56,6 +56,22 @@ class CsrGraph:
             kw[f] = getattr(self, f).to(device)
         return CsrGraph(self.n_users, self.m_items, **kw)
 
+    def entry_index(self):
+        """(entry_of_slot int64[nnz], n_entries, rev_entry int64[nnz]).  An ENTRY is a coalesced
+        (row, col) pair of A_hat — the unit the reference's edge dropout keeps or drops
+        (model/MF.py:158-166 works on the coalesced COO values, row-major like this CSR); repeated
+        slots of a multi-edge share their entry.  rev_entry[e] is the entry of (col, row): the
+        weight the transposed (backward) gather needs at slot e."""
+        if getattr(self, "_entry_index", None) is None:
+            N = self.n_nodes
+            deg = self.rowptr[1:] - self.rowptr[:-1]
+            row = torch.repeat_interleave(torch.arange(N, device=self.device), deg)
+            col = self.col.to(torch.int64)
+            uniq, inverse = torch.unique_consecutive(row * N + col, return_inverse=True)
+            rev = torch.searchsorted(uniq, col * N + row)   # exists: A is symmetric
+            self._entry_index = (inverse.contiguous(), int(uniq.numel()), rev.contiguous())
+        return self._entry_index
+
     def c_struct(self, d: int) -> _lib.GraphStruct:
         """lgcn_graph_t for embedding width d (allocates the hub scratch once)."""
         need = max(1, int(self.seg_row.numel()) * d)

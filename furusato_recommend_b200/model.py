@@ -131,6 +131,12 @@ class LightGCN(nn.Module):
         # diag(row) A diag(col); None = the graph's dinv on both sides (D^-1/2 A D^-1/2)
         self._col_scale: Optional[torch.Tensor] = None
         self._row_scale: Optional[torch.Tensor] = None
+        # edge dropout (model/MF.py:158-192; parse.py:16-17 `--dropout`, `--keepprob`): off by default
+        self.dropout = bool(config.get("dropout", 0))
+        self.keep_prob = float(config.get("keep_prob", 0.6))
+        self._drop_fwd: Optional[torch.Tensor] = None
+        self._drop_bwd: Optional[torch.Tensor] = None
+        self.dropout_mask_fn = None   # tests: callable(n_entries) -> bool mask, instead of the device RNG
         self.__init_weight()
         self.optim = FusedAdam(self.parameters(), lr=config["lr"])  # model/lgcn.py:63
         self._bufs = {}
@@ -151,6 +157,19 @@ class LightGCN(nn.Module):
         if transpose:
             return dict(src_scale=self._row_scale, dst_scale=self._col_scale)
         return dict(src_scale=self._col_scale, dst_scale=self._row_scale)
+
+    def _sample_dropout(self) -> None:
+        """One Bernoulli(keep_prob) draw per coalesced entry of A_hat, rescaled by 1/keep_prob — the
+        reference's `__dropout_x` (model/MF.py:158-166: `(rand + keep_prob).int().bool()`), drawn once
+        per propagation and shared by its K layers (MF.py:187-205).  The (i, j) and (j, i) entries
+        are dropped independently, so the backward pass uses the weights of the reverse entries."""
+        ent, n_ent, rev = self.graph.entry_index()
+        if self.dropout_mask_fn is not None:
+            m = torch.as_tensor(self.dropout_mask_fn(n_ent)).to(device=self.graph.device, dtype=torch.bool)
+        else:
+            m = (torch.rand(n_ent, device=self.graph.device) + self.keep_prob).int().bool()
+        w = m.to(torch.float32) / self.keep_prob
+        self._drop_fwd, self._drop_bwd = w[ent].contiguous(), w[rev].contiguous()
 
     def train(self, mode: bool = True):
         # weights only move in training mode; eval mode may reuse one propagation
@@ -212,13 +231,17 @@ class LightGCN(nn.Module):
         K, g = self.num_layers, self.graph
         z = [self._buf("Z0"), self._buf("Z1")]
         acc = self._buf("ACC")
+        if self.dropout and self.training:
+            self._sample_dropout()
+        else:
+            self._drop_fwd = self._drop_bwd = None
         for k in range(K):
             last = k == K - 1
             ops.propagate_layer(
                 g, emb if k == 0 else z[(k - 1) & 1], scale_src=(k == 0),
                 dst=None if last else z[k & 1],
                 acc_in=emb if k == 0 else acc, acc_out=out if last else acc,
-                acc_scale=1.0 / (K + 1) if last else 1.0, **self._scales(False))
+                acc_scale=1.0 / (K + 1) if last else 1.0, edge_w=self._drop_fwd, **self._scales(False))
 
     def _horner_into(self, G: torch.Tensor, *, grad_mode: int, reg_coef: float, cnt: torch.Tensor,
                      grad: Optional[torch.Tensor] = None, adam: Optional[dict] = None) -> None:
@@ -237,7 +260,8 @@ class LightGCN(nn.Module):
                     kw.update(adam_m=adam["exp_avg"], adam_v=adam["exp_avg_sq"], adam_hp=adam["hp"],
                               betas=adam["betas"], eps=adam["eps"], zero_base=K > 1)
             ops.propagate_layer(g, G if j == 0 else z[(j - 1) & 1], scale_src=(j == 0),
-                                dst=None if last else z[j & 1], base=G, **kw, **self._scales(True))
+                                dst=None if last else z[j & 1], base=G, edge_w=self._drop_bwd, **kw,
+                                **self._scales(True))
 
     def computer(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """Propagated (users, items) embeddings — model/MF.py:178-210 naming."""
@@ -288,7 +312,8 @@ class LightGCN(nn.Module):
         """One fused train step.  Full-size batches replay a captured CUDA graph (8 kernels, no
         per-launch host work); anything else (last partial batch, cuda_graph=False) launches eagerly."""
         B = users.numel()
-        if not self.use_cuda_graph or B != int(self.config["bpr_batch_size"]):
+        if not self.use_cuda_graph or self.dropout or B != int(self.config["bpr_batch_size"]):
+            # (a fresh dropout mask per step is drawn with torch ops: not part of the captured graph)
             return self._fused_step_eager(self._ids(users), self._ids(pos), self._ids(neg))
         self._reset_seed_buffers()  # only dirty after the autograd path; the graph assumes clean G/cnt
         lr = self.optim.param_groups[0]["lr"]

@@ -50,10 +50,12 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
                     adam_v: Optional[torch.Tensor] = None, adam_hp: Optional[torch.Tensor] = None,
                     betas=(0.9, 0.999), eps: float = 1e-8, zero_base: bool = False,
                     dst_peers: Optional[Sequence[int]] = None, dst_row_offset: int = 0,
-                    src_scale: Optional[torch.Tensor] = None, dst_scale: Optional[torch.Tensor] = None) -> None:
+                    src_scale: Optional[torch.Tensor] = None, dst_scale: Optional[torch.Tensor] = None,
+                    edge_w: Optional[torch.Tensor] = None) -> None:
     """lgcn_propagate_layer: one normalised-adjacency SpMM + fused row epilogue.
     `src_scale` / `dst_scale` ([N] fp32) replace the graph's dinv on the column / row side
-    (rAdjGCN's asymmetric normalisation); None keeps D^-1/2 A D^-1/2."""
+    (rAdjGCN's asymmetric normalisation); None keeps D^-1/2 A D^-1/2.  `edge_w` ([nnz] fp32) weights
+    every CSR slot (edge dropout)."""
     lib = _lib.load()
     n_src, d = src.shape
     N = g.n_nodes  # rows of this (possibly rank-local) graph; src may hold more rows (all-gathered)
@@ -82,6 +84,9 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
             raise ValueError(f"{nm} must be [>={N}], got {tuple(t.shape)}")
     a.src_scale = _chk(src_scale, torch.float32, "src_scale", True)
     a.dst_scale = _chk(dst_scale, torch.float32, "dst_scale", True)
+    if edge_w is not None and (edge_w.dim() != 1 or edge_w.numel() != g.nnz):
+        raise ValueError(f"edge_w must be [{g.nnz}] (one weight per CSR slot), got {tuple(edge_w.shape)}")
+    a.edge_w = _chk(edge_w, torch.float32, "edge_w", True)
     if dst_peers:
         if dst is None:
             raise ValueError("dst_peers needs dst (it fixes the dtype and enables the write)")

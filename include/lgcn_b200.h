@@ -132,6 +132,11 @@ typedef struct lgcn_layer_args {
    * call with the two vectors swapped (A itself is symmetric). */
   const float* src_scale; /* [N] fp32 or NULL */
   const float* dst_scale; /* [N] fp32 or NULL */
+  /* Per-slot weights, aligned with the graph's `col` array, or NULL: s_i = sum_e edge_w[e] * w_j *
+   * SRC[col[e]].  Edge dropout (model/MF.py:158-176: every coalesced entry of A_hat is kept with
+   * probability keep_prob and rescaled by 1/keep_prob, independently per direction) passes
+   * mask/keep_prob here; the backward pass passes the weights of the REVERSE entries. */
+  const float* edge_w;
 } lgcn_layer_args_t;
 
 int lgcn_propagate_layer(const lgcn_graph_t* g /*HOST*/, const lgcn_layer_args_t* a /*HOST*/,

@@ -574,3 +574,12 @@ def normalised_cdf(p: np.ndarray) -> np.ndarray:
     """np.random.choice's table: cdf = p.cumsum(); cdf /= cdf[-1] (float64), stored as fp32."""
     c = np.cumsum(np.asarray(p, dtype=np.float64))
     return (c / c[-1]).astype(np.float32)
+
+
+def dropout_graph(graph: torch.Tensor, mask: torch.Tensor, keep_prob: float) -> torch.Tensor:
+    """`__dropout_x` of model/MF.py:158-166 with the Bernoulli draw factored out: entries of the
+    coalesced graph where `mask` is False are removed, the others divided by keep_prob.  The
+    reference's own draw is `(torch.rand(len(values)) + keep_prob).int().bool()` (:162-163)."""
+    idx, val = graph.indices(), graph.values()
+    mask = torch.as_tensor(mask, dtype=torch.bool)
+    return torch.sparse_coo_tensor(idx[:, mask], val[mask] / keep_prob, graph.shape)

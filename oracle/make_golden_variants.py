@@ -160,6 +160,40 @@ def main():
     out["capped_philox_seed9_epoch1"] = orc.capped_sample_philox(ds.allPos, n, m, 3000, seed=9, epoch=1, limit=CAP)
     print(f"[capped sampler] {len(S_ref)} of {ds.trainDataSize * 3} triples kept, identical under MT19937 seed 321")
 
+    # edge dropout of the legacy class (model/MF.py:158-192): same torch seed -> same mask
+    from model import MF as ref_MF
+    KEEP = 0.6
+    ds.getSparseGraph = lambda: orc.sparse_graph(n, m, ds.trainUser, ds.trainItem)   # == the reference's (make_golden.py)
+    cfg_d = dict(cfg)
+    cfg_d.update(latent_dim_rec=d, lightGCN_n_layers=K, keep_prob=KEEP, A_split=False, pretrain=0, dropout=1)
+    mdl = ref_MF.LightGCN(cfg_d, ds)
+    mdl.device = "cpu"
+    with torch.no_grad():
+        mdl.embedding_user.weight.copy_(E0[:n])
+        mdl.embedding_item.weight.copy_(E0[n:])
+    mdl.train()
+    import contextlib, io
+    torch.manual_seed(99)
+    with contextlib.redirect_stdout(io.StringIO()):      # the reference prints "droping" per call
+        loss_d, reg_d = mdl.bpr_loss(tu, tp, tn)
+    mdl.optim.zero_grad()
+    (loss_d + cfg["decay"] * reg_d).backward()
+    grad_d = torch.cat([mdl.embedding_user.weight.grad, mdl.embedding_item.weight.grad]).clone()
+    g_full = ds.getSparseGraph()
+    torch.manual_seed(99)
+    mask = (torch.rand(len(g_full.values())) + KEEP).int().bool()
+    gd = orc.dropout_graph(g_full, mask, KEEP)
+    w = E0.clone().requires_grad_(True)
+    ol, orr = orc.bpr_loss(w, gd, K, n, tu, tp, tn)
+    assert ol.item() == loss_d.item() and orr.item() == reg_d.item(), "dropout: loss differs"
+    (ol + cfg["decay"] * orr).backward()
+    assert torch.allclose(w.grad, grad_d, rtol=0, atol=1e-9), "dropout: grad differs"
+    du, di = orc.computer(E0, gd, K, n)
+    out.update(dropout_keep=np.float64(KEEP), dropout_mask=mask.numpy(), dropout_users=du.numpy(), dropout_items=di.numpy(),
+               dropout_loss=loss_d.item(), dropout_reg=reg_d.item(), dropout_grad=grad_d.numpy())
+    assert 0.5 < mask.float().mean() < 0.7 and not torch.equal(gd.to_dense(), gd.to_dense().t())
+    print(f"[dropout] keep {mask.float().mean():.3f} of {len(mask)} entries (asymmetric); loss/grad match the live reference")
+
     # popularity-weighted positive pick of UniformSampling (negative_sample.py:12-69): the class
     # unpickles per-user probabilities from a fixed relative path (:22-36); feed it ours.
     import pickle

@@ -127,3 +127,39 @@ def test_weighted_positive_sampler_bit_exact(golden, variants):
     full, _ = orc.uniform_sample_philox(train, ds.n_users, ds.m_items, 3000, seed=4, epoch=2)
     assert np.array_equal(u0.cpu().numpy(), full)
     assert pop[d[:, 1].cpu().numpy()].mean() < pop[full[:, 1]].mean()
+
+
+@pytest.mark.parametrize("storage", ["fp32", "bf16"])
+def test_edge_dropout_matches_live_reference(golden, variants, storage):
+    """Edge dropout (model/MF.py:158-192) through per-slot weights: forward with the mask the live
+    reference drew, and the gradient through the TRANSPOSED dropped operator (reverse-entry weights)."""
+    keep = float(variants["dropout_keep"])
+    model = _load(LightGCN(_cfg(golden, dropout=1, keep_prob=keep, storage_dtype=storage), golden_dataset(golden)), golden)
+    mask = variants["dropout_mask"]
+    model.dropout_mask_fn = lambda n_entries: mask
+    assert model.graph.entry_index()[1] == len(mask)
+    rtol = 1e-5 if storage == "fp32" else 2e-2
+    model.train()
+    with torch.no_grad():
+        u, i = model.computer()
+    assert_close(u, variants["dropout_users"], rtol=rtol, what="dropout users")
+    assert_close(i, variants["dropout_items"], rtol=rtol, what="dropout items")
+    bu, bp, bn = batch(golden)
+    loss, reg = model.bpr_loss(bu, bp, bn)
+    assert abs(loss.item() - float(variants["dropout_loss"])) <= rtol * abs(float(variants["dropout_loss"]))
+    model.optim.zero_grad()
+    (loss + float(model.config["decay"]) * reg).backward()
+    assert_close(model.all_embedding.weight.grad, variants["dropout_grad"], rtol=rtol, what="dropout grad")
+    # eval mode never drops (MF.py:187-192), and the fused step draws a fresh mask per step
+    model.eval()
+    with torch.no_grad():
+        eu, _ = model.computer()
+    assert_close(eu, golden["computer_users"], rtol=rtol, what="eval users")
+    model.train()
+    model.dropout_mask_fn = None
+    l1 = model.stageOne(bu, bp, bn).item()
+    w1 = model._drop_fwd.clone()
+    l2 = model.stageOne(bu, bp, bn).item()
+    assert np.isfinite(l1) and np.isfinite(l2) and not torch.equal(w1, model._drop_fwd)
+    frac = float((model._drop_fwd > 0).float().mean())
+    assert abs(frac - keep) < 0.05

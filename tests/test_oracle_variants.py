@@ -112,3 +112,21 @@ def test_weighted_positive_sampler(golden, variants, tiny_lists):
     # rare items are preferred: mean popularity of the weighted positives is lower
     pop = np.bincount(golden["train_item"], minlength=m)
     assert pop[P[:, 1]].mean() < pop[U[:, 1]].mean()
+
+
+def test_edge_dropout_matches_live_reference(golden, variants):
+    """model/MF.py:158-192 with the mask the live reference drew under torch.manual_seed(99)."""
+    n, m, K, lr, decay, edge, (tu, tp, tn) = _setup(golden)
+    keep = float(variants["dropout_keep"])
+    g = orc.sparse_graph(n, m, golden["train_user"], golden["train_item"])
+    torch.manual_seed(99)
+    mask = (torch.rand(len(g.values())) + keep).int().bool()       # MF.py:162-163
+    assert np.array_equal(mask.numpy(), variants["dropout_mask"])
+    gd = orc.dropout_graph(g, mask, keep)
+    w = torch.from_numpy(golden["E0"]).clone().requires_grad_(True)
+    u, i = orc.computer(w, gd, K, n)
+    assert np.array_equal(u.detach().numpy(), variants["dropout_users"])
+    loss, reg = orc.bpr_loss(w, gd, K, n, tu, tp, tn)
+    assert loss.item() == float(variants["dropout_loss"]) and reg.item() == float(variants["dropout_reg"])
+    (loss + decay * reg).backward()
+    assert np.allclose(w.grad.numpy(), variants["dropout_grad"], rtol=0, atol=1e-9)
