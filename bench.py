@@ -144,12 +144,20 @@ def cpu_train_steps(ds_arrays, steps: int, warmup: int, threads: int):
     return sum(times) / len(times)
 
 
+def workload_name(tag: str, world: int, K: int, d: int, B: int, n: int, m: int, nnz: int) -> str:
+    """config.workload of both arms (the driver compares them)."""
+    return (f"{tag}{' x%d' % world if world > 1 and tag == 'cfg-2' else ''}: LightGCN {K}-layer d={d} BPR B={B} on a synthetic "
+            f"five-core bipartite graph {n} users x {m} items, nnz(A_hat)={nnz}")
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
     import torch
     from furusato_recommend_b200.synthetic import bipartite
-    n, m, tu, ti, su, si = bipartite(CFG2["n_users"], CFG2["m_items"], CFG2["n_interactions"], seed=CFG2["seed"])
+    world = max(1, int(args.gpus))   # the same graph our arm trains on at this N (cfg-2 x N, weak scaling)
+    n, m, tu, ti, su, si = bipartite(CFG2["n_users"] * world, CFG2["m_items"] * world, CFG2["n_interactions"] * world,
+                                     seed=CFG2["seed"])
     nnz = 2 * int(tu.numel())
     threads = os.cpu_count() or 1
     steps = max(1, min(args.steps, 10))  # ~1 s per CPU step: keep the arm within a few minutes
@@ -161,8 +169,8 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg-2: LightGCN 3-layer d=64 BPR B=2048, synthetic five-core bipartite graph "
-                               f"{n}x{m}, nnz={nnz}", "path": "reference CPU path (oracle port, torch.sparse)"},
+        "config": {"workload": workload_name("cfg-2", world, CFG2["layers"], CFG2["d"], CFG2["batch"], n, m, nnz),
+                   "path": "reference CPU path (oracle port, torch.sparse) on the host cores of rank 0"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -421,8 +429,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "scaling": "weak" if args.workload == "cfg2" else "strong", "vs_baseline": None,
             "dtype": "f32" if args.storage == "fp32" else "bf16-storage/f32-acc",
             "data": "synthetic",
-            "config": {"workload": f"{ {'hbm': 'hbm-bound', 'cfg3': 'cfg-3', 'cfg2': 'cfg-2', 'cfg4': 'cfg-4 (lgcnssm, %d negatives per positive)' % J}[args.workload] }{' x%d' % world if world > 1 and args.workload == 'cfg2' else ''}: LightGCN {K}-layer d={d} BPR B={B} on a synthetic "
-                                   f"five-core bipartite graph {n} users x {m} items, nnz(A_hat)={nnz}",
+            "config": {"workload": workload_name({'hbm': 'hbm-bound', 'cfg3': 'cfg-3', 'cfg2': 'cfg-2',
+                                                  'cfg4': 'cfg-4 (lgcnssm, %d negatives per positive)' % J}[args.workload],
+                                                 world, K, d, B, n, m, nnz),
                        "l2": "256 MiB buffer written between timed steps (L2 flush, untimed)",
                        "parallelism": "1 GPU" if world == 1 else
                        f"{world} GPUs: rows partitioned by nnz; per-layer exchange = " +
