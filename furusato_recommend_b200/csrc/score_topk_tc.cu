@@ -33,6 +33,11 @@
 
 #include <string>
 
+// Build with -DLGCN_TC_RS=1 to compile the experimental register-staged epilogue (layout "m2rs").
+#ifndef LGCN_TC_RS
+#define LGCN_TC_RS 0
+#endif
+
 #include "common.cuh"
 
 namespace lgcn {
@@ -282,6 +287,20 @@ __device__ __forceinline__ float max32_h(const uint32_t (&r)[32], float (&m4)[4]
   return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
 }
 
+// r[c] for a warp-uniform c: a dense switch (jump table), no dynamic register indexing
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&r)[32], int c) {
+  uint32_t v = 0;
+  switch (c) {
+#define LGCN_PICK(i) case i: v = r[i]; break;
+    LGCN_PICK(0) LGCN_PICK(1) LGCN_PICK(2) LGCN_PICK(3) LGCN_PICK(4) LGCN_PICK(5) LGCN_PICK(6) LGCN_PICK(7)
+    LGCN_PICK(8) LGCN_PICK(9) LGCN_PICK(10) LGCN_PICK(11) LGCN_PICK(12) LGCN_PICK(13) LGCN_PICK(14) LGCN_PICK(15)
+    LGCN_PICK(16) LGCN_PICK(17) LGCN_PICK(18) LGCN_PICK(19) LGCN_PICK(20) LGCN_PICK(21) LGCN_PICK(22) LGCN_PICK(23)
+    LGCN_PICK(24) LGCN_PICK(25) LGCN_PICK(26) LGCN_PICK(27) LGCN_PICK(28) LGCN_PICK(29) LGCN_PICK(30) LGCN_PICK(31)
+#undef LGCN_PICK
+  }
+  return v;
+}
+
 struct Params {
   const uint4* a_packed;   // user tiles, [n_utiles][D/8][128]
   const uint4* b_packed;   // item tiles, [n_itiles][D/8][TN]
@@ -307,9 +326,14 @@ struct Params {
 // NST accumulator stages in TMEM: an epilogue warp that runs into candidates (the rare slow path)
 // only holds back ITS stage; with 4 stages the other warps and the MMA issuer run ahead and the
 // variance averages out instead of costing every tile the slowest warp's time.
-template <int D, int TN, int GROUPS, bool DUMP, bool ACC16, int MT, int NST>
+// RS ("register-staged", EXPERIMENTAL, not the default — untested on hardware at the end of round 1):
+// the epilogue copies the whole 128-column accumulator of its user tile into registers and hands the
+// TMEM stage back BEFORE any selection work, so the MMA never waits for a warp that ran into
+// candidates; candidate values are then picked from registers with a warp-uniform switch.
+template <int D, int TN, int GROUPS, bool DUMP, bool ACC16, int MT, int NST, bool RS = false>
 __global__ void __launch_bounds__((kFrontWarps + 4 * GROUPS) * 32, 1)
 score_topk_tc_kernel(const Params p) {
+  static_assert(!RS || (!ACC16 && GROUPS == MT && TN == 128), "register staging: fp32, one group per user tile, TN 128");
   constexpr int NT = GROUPS * 128;              // epilogue threads
   constexpr int CG = GROUPS / MT;               // column groups per user tile
   constexpr int kTmemCols = NST * MT * TN;
@@ -450,6 +474,75 @@ score_topk_tc_kernel(const Params p) {
     static_assert(CPG >= 1 && CPG * COLS * CG == TN, "every epilogue group needs whole chunks of the tile");
     const int c0 = cg * CPG;
 
+#if LGCN_TC_RS
+    if constexpr (RS) {
+      for (int j = 0; j < n_tiles; ++j) {
+        const int a = j % NST;
+        mbar_wait(bar_tfull + 8 * (a * MT + mt), (j / NST) & 1);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + lane_base + (uint32_t)((a * MT + mt) * TN);
+        uint32_t r[4][32];
+        __syncwarp();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) tc_ld32(tbase + (uint32_t)(32 * q4), r[q4]);
+        tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * (a * MT + mt));   // the accumulator lives in registers now
+        const int item_tile0 = j * TN;
+        if (DUMP) {
+          if (live) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (item_tile0 + 32 * q4 + i < p.m_items)
+                  p.dense[grow * p.m_items + item_tile0 + 32 * q4 + i] = __uint_as_float(r[q4][i]);
+          }
+        }
+        float m4[4][4], cm[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) cm[q4] = max32(r[q4], m4[q4]);
+        if (__any_sync(0xffffffffu, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) > sel.thr)) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (!__any_sync(0xffffffffu, cm[q4] > sel.thr)) continue;
+            uint32_t hm = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              if (__any_sync(0xffffffffu, m4[q4][b] > sel.thr)) {
+#pragma unroll
+                for (int i = 8 * b; i < 8 * b + 8; ++i) hm |= (__uint_as_float(r[q4][i]) > sel.thr) ? (1u << i) : 0u;
+              }
+            }
+            uint32_t any = __reduce_or_sync(0xffffffffu, hm);
+            while (any) {
+              const int c = __ffs(any) - 1;
+              any &= any - 1;
+              __syncwarp();
+              const uint32_t raw = pick32(r[q4], c);
+              if ((hm >> c) & 1u) {
+                const int item = item_tile0 + 32 * q4 + c;
+                while (next_pos < item) {   // walk of the sorted train positives (ascending sweep)
+                  ++pp;
+                  next_pos = pp < my_npos ? __ldg(my_pos + pp) : 0x7fffffff;
+                }
+                const float v = next_pos == item ? p.mask_value : __uint_as_float(raw);  // trainer.py:137
+                if (item < p.m_items && v > sel.thr) {
+                  if (sel.cnt == p.cap) sel = sel_compact(sel, mv, mi, NT, p.k);
+                  if (v > sel.thr) {
+                    mv[sel.cnt * NT] = v;
+                    mi[sel.cnt * NT] = item;
+                    ++sel.cnt;
+                  }
+                }
+              }
+            }
+          }
+          if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
+        }
+      }
+    } else
+#endif
     for (int j = 0; j < n_tiles; ++j) {
       const int a = j % NST;
       mbar_wait(bar_tfull + 8 * (a * MT + mt), (j / NST) & 1);
@@ -618,7 +711,7 @@ score_topk_tc_kernel(const Params p) {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 
-template <int D, int TN, int GROUPS, int MT, int NST>
+template <int D, int TN, int GROUPS, int MT, int NST, bool RS = false>
 static int launch(const Params& p0, cudaStream_t st) {
   Params p = p0;
   constexpr int NT = GROUPS * 128;
@@ -637,7 +730,7 @@ static int launch(const Params& p0, cudaStream_t st) {
   const int threads = (kFrontWarps + 4 * GROUPS) * 32;
 #define LGCN_TC_LAUNCH(DUMP_, ACC_)                                                                     \
   do {                                                                                                    \
-    auto kern = score_topk_tc_kernel<D, TN, GROUPS, DUMP_, ACC_, MT, NST>;                                \
+    auto kern = score_topk_tc_kernel<D, TN, GROUPS, DUMP_, ACC_, MT, NST, RS && !ACC_>;                   \
     LGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     kern<<<grid, threads, smem, st>>>(p);                                                                 \
   } while (0)
@@ -663,7 +756,7 @@ static size_t smem_need(int d, int tn, int groups, int mt, int cap) {
 }
 
 // One configuration: pack both operands for (TN, MT) and launch.
-template <int D, int TN, int GROUPS, int MT, int NST>
+template <int D, int TN, int GROUPS, int MT, int NST, bool RS = false>
 static int run_cfg(const float* user_emb, const float* item_emb, const int64_t* user_ids, int n_eval,
                    int m_items, const int64_t* pos_rowptr, const int32_t* pos_sorted, int k, int cap,
                    float mask_value, int32_t* out_idx, float* out_val, float* dense, void* workspace,
@@ -712,7 +805,7 @@ static int run_cfg(const float* user_emb, const float* item_emb, const int64_t* 
     const char* tg = getenv("LGCN_TC_TRIG");
     p.trig = tg ? atoi(tg) : 0;
   }
-  return launch<D, TN, GROUPS, MT, NST>(p, st);
+  return launch<D, TN, GROUPS, MT, NST, RS>(p, st);
 }
 
 #define LGCN_TC_ARGS user_emb, item_emb, user_ids, n_eval, m_items, pos_rowptr, pos_sorted, k
@@ -737,6 +830,9 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
   const std::string layout = le ? le : "auto";
   if constexpr (D <= 64) {
     if (k <= 24 && !acc16) {
+#if LGCN_TC_RS
+      if (layout == "m2rs") return run_cfg<D, 128, 2, 2, 2, true>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
+#endif
       if (layout == "m2g2" || layout == "auto") return run_cfg<D, 128, 2, 2, 2>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
     }
     if (k <= 20 && !acc16 && layout == "m2g4") return run_cfg<D, 128, 4, 2, 2>(LGCN_TC_ARGS, 32, LGCN_TC_TAIL);
