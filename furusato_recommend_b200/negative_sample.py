@@ -48,6 +48,22 @@ POSITIVE_NUM_LIMIT = 3000   # ddp_lgcn.py:34
 TRAIN_ITERATIVE = 3         # ddp_lgcn.py:35
 
 
+def cap_keep_mask(pos: torch.Tensor, valid: torch.Tensor, m_items: int, limit: int) -> torch.Tensor:
+    """uint8[count]: 1 where the sample is valid and fewer than `limit` valid samples of LOWER index
+    carry the same positive item (the order-dependent counter of ddp_lgcn.py:569-570 as a rank)."""
+    count = pos.numel()
+    key = torch.where(valid.bool(), pos, torch.full_like(pos, m_items))  # empties sort last
+    skey, order = torch.sort(key, stable=True)
+    pos_in_sorted = torch.arange(count, device=key.device)
+    run_start = torch.zeros(m_items + 2, dtype=torch.int64, device=key.device)
+    run_start[1:] = torch.cumsum(torch.bincount(skey, minlength=m_items + 1), 0)
+    rank = pos_in_sorted - run_start[skey]
+    keep_sorted = (rank < limit) & (skey < m_items)
+    keep = torch.zeros(count, dtype=torch.uint8, device=key.device)
+    keep[order] = keep_sorted.to(torch.uint8)
+    return keep
+
+
 def UniformSampleCapped(dataset, neg_ratio: int = 1, *, limit: int = POSITIVE_NUM_LIMIT,
                         iterative: int = TRAIN_ITERATIVE, seed: int | None = None, epoch: int | None = None,
                         count: int | None = None) -> torch.Tensor:
@@ -68,16 +84,7 @@ def UniformSampleCapped(dataset, neg_ratio: int = 1, *, limit: int = POSITIVE_NU
     rowptr, file_items, sorted_items = dataset.pos_csr()
     triples, valid = ops.uniform_sample(rowptr, file_items, sorted_items, dataset.n_users, dataset.m_items,
                                         count, seed, epoch)
-    m = int(dataset.m_items)
-    key = torch.where(valid.bool(), triples[:, 1], torch.full_like(triples[:, 1], m))  # empties sort last
-    skey, order = torch.sort(key, stable=True)
-    pos_in_sorted = torch.arange(count, device=key.device)
-    run_start = torch.zeros(m + 2, dtype=torch.int64, device=key.device)
-    run_start[1:] = torch.cumsum(torch.bincount(skey, minlength=m + 1), 0)
-    rank = pos_in_sorted - run_start[skey]
-    keep_sorted = (rank < int(limit)) & (skey < m)
-    keep = torch.zeros(count, dtype=torch.uint8, device=key.device)
-    keep[order] = keep_sorted.to(torch.uint8)
+    keep = cap_keep_mask(triples[:, 1], valid, int(dataset.m_items), int(limit))
     return ops.compact_triples(triples, keep)
 
 

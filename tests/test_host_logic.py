@@ -152,3 +152,52 @@ def test_synthetic_generator_shape():
     assert 0.78 < frac < 0.86
     n2, m2, tu2, *_ = bipartite(2000, 3000, 60000, seed=1)
     assert (n2, m2) == (n, m) and torch.equal(tu, tu2)
+
+
+def test_cap_keep_mask_is_the_sequential_counter():
+    """ddp_lgcn.py:569-570 (a dict counted along the loop) == rank among earlier samples with the same positive."""
+    from furusato_recommend_b200.negative_sample import cap_keep_mask
+    rng = np.random.default_rng(3)
+    m, count, limit = 17, 500, 4
+    pos = rng.integers(0, m, count)
+    valid = rng.random(count) > 0.2
+    pos_t = torch.from_numpy(np.where(valid, pos, -1))
+    keep = cap_keep_mask(pos_t, torch.from_numpy(valid.astype(np.uint8)), m, limit).numpy().astype(bool)
+    want, oc = np.zeros(count, dtype=bool), {}
+    for i in range(count):
+        if valid[i] and oc.get(pos[i], 0) < limit:
+            oc[pos[i]] = oc.get(pos[i], 0) + 1
+            want[i] = True
+    assert np.array_equal(keep, want) and keep.sum() == sum(min(limit, int((pos[valid] == v).sum())) for v in range(m))
+
+
+def test_segment_cdf_matches_numpy_choice_table():
+    from furusato_recommend_b200.negative_sample import _segment_cdf
+    rng = np.random.default_rng(4)
+    lens = np.array([3, 0, 1, 7, 0, 5])
+    rowptr = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]))
+    w = rng.random(lens.sum()) + 0.01
+    cdf = _segment_cdf(torch.from_numpy(w), rowptr).numpy()
+    o = 0
+    for n in lens:
+        if n:
+            want = orc.normalised_cdf(w[o:o + n])       # np.random.choice: cumsum / cumsum[-1]
+            assert np.abs(cdf[o:o + n] - want).max() < 1e-6 and abs(cdf[o + n - 1] - 1.0) < 1e-6
+            assert np.all(np.diff(cdf[o:o + n]) > 0)
+        o += n
+
+
+def test_entry_index_groups_multi_edges_and_finds_reverse_entries(golden):
+    n, m = int(golden["n_users"]), int(golden["m_items"])
+    g = G.build_csr_graph(n, m, torch.from_numpy(golden["train_user"]), torch.from_numpy(golden["train_item"]))
+    ent, n_ent, rev = g.entry_index()
+    assert n_ent == len(golden["adj_val"])                      # one entry per coalesced COO value of the reference
+    assert int(ent.max()) == n_ent - 1 and g.nnz > n_ent         # the tiny graph has multi-edges
+    N = n + m
+    deg = g.rowptr[1:] - g.rowptr[:-1]
+    row = torch.repeat_interleave(torch.arange(N), deg)
+    col = g.col.long()
+    er = torch.zeros(n_ent, dtype=torch.int64).scatter_(0, ent, row)
+    ec = torch.zeros(n_ent, dtype=torch.int64).scatter_(0, ent, col)
+    assert torch.equal(er, torch.from_numpy(golden["adj_row"])) and torch.equal(ec, torch.from_numpy(golden["adj_col"]))
+    assert torch.equal(er[rev], col) and torch.equal(ec[rev], row)   # rev[e] is the entry (col, row) of slot e
