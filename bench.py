@@ -418,6 +418,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         s_bytes = 2 if args.storage == "bf16" else 4
         layer_bytes = spmm_layer_bytes(nnz // world, N // world, d, s_bytes)  # per rank, per launch
         achieved = layer_bytes / spmm_avg_s / 1e9
+        n_loc, nnz_loc = N // world, nnz // world
+        compulsory = nnz_loc * 4 + (n_loc + 1) * 8 + 2 * n_loc * d * s_bytes
+        gather_ceiling = 19800.0 if n_loc * d * s_bytes < 100e6 else 7200.0
         traffic = None
         tp = REPO / "profiles" / "spmm_traffic.json"
         if tp.exists():
@@ -448,6 +451,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which,
                          "bytes_per_launch": layer_bytes, "avg_launch_us": spmm_avg_s * 1e6,
                          "launches_per_step": 2 * K,
+                         # SURVEY 8d caveat: with an L2-resident table the gather term never reaches DRAM, so also
+                         # report the compulsory DRAM bytes (col ids + rowptr + read/write of the [N, d] rows) and the
+                         # measured ceiling of this access pattern (tools/gather_ceiling.cu: 19.8 TB/s from L2,
+                         # 7.2 TB/s from HBM) the kernel is really up against
+                         "compulsory_bytes_per_launch": compulsory,
+                         "compulsory_gbs": compulsory / spmm_avg_s / 1e9,
+                         "gather_ceiling_gbs": gather_ceiling,
+                         "frac_of_gather_ceiling": achieved / gather_ceiling,
                          "note": ("gather model; the table is %.0f MB" % (N * d * s_bytes / 1e6)) +
                                  (" (L2-resident, so frac may exceed 1)" if N * d * s_bytes < 100e6 else " (>> 126 MB L2)")},
             "clocks": clk,
