@@ -150,6 +150,14 @@ class RowPartition:
         return torch.cat(parts)
 
 
+def build_g0(full: torch.Tensor, dinv_pad: torch.Tensor, ids: torch.Tensor, G_c: torch.Tensor) -> None:
+    """full[W*R, d] = dinv (.) G for a gradient seed G that is non-zero only in the rows `ids` (padded
+    ids, duplicates add) — the pre-scaled layer-0 source of the backward pass, built LOCALLY from the
+    compact BPR table every rank already holds, instead of exchanging the (almost empty) G shards."""
+    full.zero_()
+    full.index_add_(0, ids, (dinv_pad[ids][:, None] * G_c).to(full.dtype))
+
+
 # local_spmm(src_full [W*R, d], *, dst, base, acc_in, acc_out, acc_scale, last_kwargs) -> None
 LocalSpmm = Callable[..., None]
 
@@ -199,15 +207,21 @@ class DistPropagator:
                       acc_scale=1.0 / (K + 1) if last else 1.0)
             src = z[k & 1]
 
-    def backward(self, G_local: torch.Tensor, **last_kwargs) -> None:
+    def backward(self, G_local: torch.Tensor, g0=None, **last_kwargs) -> None:
         """H0 = G, H_{j+1} = G + A_hat H_j; the last layer's epilogue consumes H_K
-        (grad_mode 1 or 2 keyword arguments are passed through to the local op)."""
+        (grad_mode 1 or 2 keyword arguments are passed through to the local op).
+        g0 = (dinv_pad [W*R], ids [n], G_c [n, d]): build the first layer's gathered source locally
+        (`build_g0`) instead of all-gathering dinv (.) G."""
         K = self.K
-        _, z = self._buffers(G_local.shape[1], G_local.device)
-        src = (self.dinv[:, None] * G_local).to(self.storage_dtype)
+        full0, z = self._buffers(G_local.shape[1], G_local.device)
+        src = None if g0 is not None else (self.dinv[:, None] * G_local).to(self.storage_dtype)
         for j in range(K):
             last = j == K - 1
-            full = self._gather(src)
+            if j == 0 and g0 is not None:
+                build_g0(full0, *g0)
+                full = full0
+            else:
+                full = self._gather(src)
             kw = last_kwargs if last else {}
             self.spmm(full, dst=None if last else z[j & 1], base=G_local, acc_in=None, acc_out=None,
                       acc_scale=1.0, **kw)
@@ -241,11 +255,17 @@ class PushPropagator:
     def _barrier(self):
         self.hdl[0].barrier(channel=0)
 
-    def _run(self, first_src: torch.Tensor, layer_kwargs):
+    def _run(self, first_src: torch.Tensor, layer_kwargs, g0=None):
         ops, K = self.ops, self.K
-        self._barrier()  # every peer is done reading buf[0] (last layer of the previous pass)
-        ops.scale_rows_push(first_src, self.dinv, self.storage_dtype, self.peers[0], self.row0)
-        self._barrier()
+        if g0 is not None:
+            # Backward pass with a sparse seed: the layer-0 source is built in this rank's OWN buffer, no
+            # exchange.  The caller guarantees a cross-GPU barrier between the previous pass and this one
+            # (the BPR row exchange has one), so no peer still reads the buffer layer 0 pushes into.
+            build_g0(self.bufs[0], *g0)
+        else:
+            self._barrier()  # every peer is done reading buf[0] (last layer of the previous pass)
+            ops.scale_rows_push(first_src, self.dinv, self.storage_dtype, self.peers[0], self.row0)
+            self._barrier()
         for k in range(K):
             last = k == K - 1
             nxt = (k + 1) & 1
@@ -262,8 +282,8 @@ class PushPropagator:
             acc_in=emb_local if k == 0 else acc, acc_out=out if last else acc,
             acc_scale=1.0 / (K + 1) if last else 1.0))
 
-    def backward(self, G_local: torch.Tensor, **last_kwargs) -> None:
-        self._run(G_local, lambda k, last: dict(base=G_local, **(last_kwargs if last else {})))
+    def backward(self, G_local: torch.Tensor, g0=None, **last_kwargs) -> None:
+        self._run(G_local, lambda k, last: dict(base=G_local, **(last_kwargs if last else {})), g0=g0)
 
 
 def exchange_rows(part: RowPartition, rank: int, local, padded_ids: torch.Tensor, group=None):
@@ -336,6 +356,13 @@ class DistLightGCN:
         if self.prop is None:
             self.prop = DistPropagator(self.part, rank, dl, self.K, self._local_spmm, group, storage)
         self.collectives_per_step = 2 * self.K + 1
+        # EXPERIMENTAL (default off, CPU-tested index logic only): build the backward pass's layer-0 source
+        # locally from the compact BPR table instead of exchanging the G shards (fp32 storage only)
+        self.sparse_g0 = bool(config.get("dist_sparse_g0", False)) and storage == torch.float32 and world > 1
+        self._dinv_pad = None
+        if self.sparse_g0:
+            self._dinv_pad = torch.zeros(world * R, dtype=torch.float32, device=dev)
+            self._dinv_pad[self.part.to_padded(torch.arange(self.n + self.m, device=dev))] = g.dinv
         self._ar = None
         self._xbuf = None
         # Capturing NCCL collectives into a CUDA graph deadlocked on the 2-GPU box (round 1), so the
@@ -423,7 +450,8 @@ class DistLightGCN:
         self.G.index_add_(0, loc, torch.where(mine[:, None], G_c, torch.zeros((), dtype=G_c.dtype, device=G_c.device)))
         self.cnt.index_add_(0, loc, cnt_c * mine.to(cnt_c.dtype))
         ops.adam_tick(self.step_t, self.hp, float(self.config["lr"]))
-        self.prop.backward(self.G, grad_mode=2, inv_layers=1.0 / (self.K + 1), reg_coef=decay / B, cnt=self.cnt,
+        g0 = (self._dinv_pad, ids, G_c) if self.sparse_g0 else None
+        self.prop.backward(self.G, g0=g0, grad_mode=2, inv_layers=1.0 / (self.K + 1), reg_coef=decay / B, cnt=self.cnt,
                            emb=self.emb, adam_m=self.m1, adam_v=self.v1, adam_hp=self.hp, zero_base=False)
         self.G.zero_()
         return self.loss_out[2]

@@ -84,7 +84,21 @@ def _worker(rank, world, port, ret, side_split=False):
         ids = part.to_padded(torch.tensor([0, n + 3, 5, n + m - 1, 5, 299, n]))
         rows, mine = exchange_rows(part, rank, emb, ids)
         err_x = float((rows - E[torch.tensor([0, n + 3, 5, n + m - 1, 5, 299, n])]).abs().max())
-        ret[rank] = (err_f, err_b, err_x, int(mine.sum()), part.R, [c.tolist() for c in part.cuts])
+        # sparse seed (the BPR step's <= 3B rows, duplicates included): building the first layer's
+        # gathered source locally (g0) == exchanging dinv (.) G
+        gids = torch.tensor([0, n + 3, 5, n + m - 1, 5, 299, n])
+        G_c = torch.randn((len(gids), E.shape[1]), generator=gen)
+        pad = part.to_padded(gids)
+        own = (pad // part.R) == rank
+        Gs = torch.zeros_like(emb).index_add_(0, pad % part.R, torch.where(own[:, None], G_c, torch.zeros(())))
+        dinv_pad = torch.zeros(world * part.R)
+        dinv_pad[part.to_padded(torch.arange(n + m))] = csr.dinv
+        ga, gb = torch.empty_like(Gs), torch.empty_like(Gs)
+        kw = dict(grad_mode=1, inv_layers=1.0 / (K + 1), reg_coef=0.0, cnt=torch.zeros(part.R, dtype=torch.int32), emb=emb)
+        prop.backward(Gs, grad=ga, **kw)
+        prop.backward(Gs, g0=(dinv_pad, pad, G_c), grad=gb, **kw)
+        err_g0 = float((ga - gb).abs().max() / ga.abs().max())
+        ret[rank] = (err_f, err_b, err_x, int(mine.sum()), part.R, [c.tolist() for c in part.cuts], err_g0)
     finally:
         dist.destroy_process_group()
 
@@ -145,8 +159,9 @@ def test_partitioned_propagation_world2_gloo(side_split):
         mp.spawn(_worker, args=(world, port, ret, side_split), nprocs=world, join=True)
         assert len(ret) == world
         for rank in range(world):
-            err_f, err_b, err_x, n_mine, R, starts = ret[rank]
+            err_f, err_b, err_x, n_mine, R, starts, err_g0 = ret[rank]
             assert err_f < 1e-5, f"forward mismatch on rank {rank}: {err_f}"
             assert err_b < 1e-5, f"backward mismatch on rank {rank}: {err_b}"
             assert err_x == 0.0
+            assert err_g0 < 1e-6, f"local layer-0 source differs from the exchanged one on rank {rank}: {err_g0}"
         assert ret[0][3] + ret[1][3] == 7 and ret[0][5] == ret[1][5]
