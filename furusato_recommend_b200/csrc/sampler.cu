@@ -76,9 +76,15 @@ uniform_sample_kernel(const int64_t* __restrict__ pos_rowptr, const int32_t* __r
   const int64_t positem = pos_cdf != nullptr ? pos_file[b + pick_by_cdf(pos_cdf + b, len, r[1])]
                                              : pos_file[b + __umulhi(r[1], (uint32_t)len)];
   uint32_t j = 2, blk = 0;
+  bool exhausted = false;
   for (int t = 0; t < n_neg; ++t) {   // n_neg > 1: the sampled-softmax layout, flat (u, pos, neg_t) rows
-    int32_t negitem;
-    for (;;) {
+    int32_t negitem = -1;
+    // The reference's `while True` (negative_sample.py:121-126) never ends for a user whose positives
+    // cover every item; on the host that is a Ctrl-C, on the GPU a wedged device.  After
+    // LGCN_MAX_NEG_TRIES rejected candidates in a row the sample (and the rest of its negatives) is
+    // dropped like an empty user.  With deg(u) <= m/2 the odds of that are < 2^-256: parity untouched.
+    for (int tries = 0; !exhausted; ++tries) {
+      if (tries == LGCN_MAX_NEG_TRIES) { exhausted = true; break; }
       if ((j >> 2) != blk) {
         blk = j >> 2;
         r[0] = (uint32_t)(i & 0xffffffffu); r[1] = (uint32_t)((uint64_t)i >> 32); r[2] = blk; r[3] = epoch;
@@ -88,8 +94,10 @@ uniform_sample_kernel(const int64_t* __restrict__ pos_rowptr, const int32_t* __r
       ++j;
       if (!contains_sorted(pos_sorted + b, len, negitem)) break;
     }
-    vo[t] = 1;
-    o[3 * t] = user; o[3 * t + 1] = positem; o[3 * t + 2] = negitem;
+    vo[t] = exhausted ? 0 : 1;
+    o[3 * t] = user;
+    o[3 * t + 1] = exhausted ? -1 : positem;
+    o[3 * t + 2] = exhausted ? -1 : negitem;
   }
 }
 

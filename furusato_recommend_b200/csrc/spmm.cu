@@ -98,6 +98,7 @@ struct EpiDev {
   const float* adam_hp;
   float one_minus_b1, beta2, one_minus_b2, eps;
   int zero_base;
+  int push_emb;
   int n_peer;
   int64_t dst_row_off;
   void* peer[LGCN_MAX_PEERS];
@@ -218,6 +219,36 @@ __device__ __forceinline__ RowPre<EPL> row_prefetch(const EpiDev& p, int64_t row
   return r;
 }
 
+// dst[row] = z.  n_peer == 0: plain local store.  n_peer > 0: the all-gather is fused here — the row
+// goes to every reader's gathered buffer over NVLink (peer-mapped pointers), at this rank's row block.
+template <int D, int EPL, bool DST_BF16>
+__device__ __forceinline__ void store_dst_row(const EpiDev& p, int64_t row, int lig, const float (&z)[EPL]) {
+  const int n_dst = p.n_peer > 0 ? p.n_peer : 1;
+  const int64_t doff = p.n_peer > 0 ? (p.dst_row_off + row) * D + lig * EPL : row * D + lig * EPL;
+  for (int q = 0; q < n_dst; ++q) {
+    void* base_ptr = p.n_peer > 0 ? p.peer[q] : p.dst;
+    if (DST_BF16) {
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(base_ptr) + doff;
+      if (EPL == 8) {
+        float z8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z8[j] = z[j % EPL];
+        st_u4(dp, pack_bf16x8(z8));
+      } else {
+        uint2 w2;
+        w2.x = pack_bf16x2(z[0], z[1]);
+        w2.y = pack_bf16x2(z[2], z[3]);
+        *reinterpret_cast<uint2*>(dp) = w2;
+      }
+    } else {
+      float* dp = reinterpret_cast<float*>(base_ptr) + doff;
+#pragma unroll
+      for (int qq = 0; qq < EPL / 4; ++qq)
+        st_f4(dp + 4 * qq, make_float4(z[4 * qq], z[4 * qq + 1], z[4 * qq + 2], z[4 * qq + 3]));
+    }
+  }
+}
+
 template <int D, int EPL, bool DST_BF16>
 __device__ __forceinline__ void row_epilogue(const EpiDev& p, const RowPre<EPL>& pre, int64_t row,
                                              int lig, unsigned gmask, const float (&s)[EPL]) {
@@ -235,36 +266,12 @@ __device__ __forceinline__ void row_epilogue(const EpiDev& p, const RowPre<EPL>&
     for (int j = 0; j < EPL; ++j) t[j] = x[j];
   }
 
-  if (p.dst != nullptr) {
+  // grad_mode 2 with push_emb: dst receives the pre-scaled UPDATED embedding row instead (below)
+  if (p.dst != nullptr && !(p.grad_mode == 2 && p.push_emb)) {
     float z[EPL];
 #pragma unroll
     for (int j = 0; j < EPL; ++j) z[j] = pre.ds * t[j];
-    // n_peer == 0: plain local store.  n_peer > 0: the all-gather is fused here — the row goes to
-    // every rank's gathered buffer over NVLink (peer-mapped pointers), at this rank's row block.
-    const int n_dst = p.n_peer > 0 ? p.n_peer : 1;
-    const int64_t doff = p.n_peer > 0 ? (p.dst_row_off + row) * D + lig * EPL : off;
-    for (int q = 0; q < n_dst; ++q) {
-      void* base_ptr = p.n_peer > 0 ? p.peer[q] : p.dst;
-      if (DST_BF16) {
-        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(base_ptr) + doff;
-        if (EPL == 8) {
-          float z8[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) z8[j] = z[j % EPL];
-          st_u4(dp, pack_bf16x8(z8));
-        } else {
-          uint2 w2;
-          w2.x = pack_bf16x2(z[0], z[1]);
-          w2.y = pack_bf16x2(z[2], z[3]);
-          *reinterpret_cast<uint2*>(dp) = w2;
-        }
-      } else {
-        float* dp = reinterpret_cast<float*>(base_ptr) + doff;
-#pragma unroll
-        for (int qq = 0; qq < EPL / 4; ++qq)
-          st_f4(dp + 4 * qq, make_float4(z[4 * qq], z[4 * qq + 1], z[4 * qq + 2], z[4 * qq + 3]));
-      }
-    }
+    store_dst_row<D, EPL, DST_BF16>(p, row, lig, z);
   }
 
   if (p.acc_out != nullptr) {  // base == nullptr on this path, so pre.v holds acc_in[row]
@@ -284,6 +291,7 @@ __device__ __forceinline__ void row_epilogue(const EpiDev& p, const RowPre<EPL>&
       step_size = __ldg(p.adam_hp);
       bc2_sqrt = __ldg(p.adam_hp + 1);
     }
+    float znew[EPL];   // push_emb: src_scale[row] * updated embedding
 #pragma unroll
     for (int q = 0; q < EPL / 4; ++q) {
       const float4 e4 = ld_f4(p.emb + off + 4 * q);
@@ -309,11 +317,15 @@ __device__ __forceinline__ void row_epilogue(const EpiDev& p, const RowPre<EPL>&
         st_f4(p.adam_m + off + 4 * q, make_float4(m[0], m[1], m[2], m[3]));
         st_f4(p.adam_v + off + 4 * q, make_float4(v[0], v[1], v[2], v[3]));
         st_f4(p.emb + off + 4 * q, make_float4(en[0], en[1], en[2], en[3]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) znew[4 * q + j] = pre.ds * en[j];
         if (p.zero_base)  // leave G clean for the next step's scatter
           st_f4(const_cast<float*>(p.base) + off + 4 * q, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
     if (p.grad_mode == 2) {
+      // next step's pre-scaled layer-0 source, straight from the registers that hold the new row
+      if (p.push_emb && p.dst != nullptr) store_dst_row<D, EPL, DST_BF16>(p, row, lig, znew);
       __syncwarp(gmask);  // every lane of the group has read cnt[row]
       if (lig == 0) p.cnt[row] = 0;
     }
@@ -572,6 +584,8 @@ extern "C" int lgcn_propagate_layer(const lgcn_graph_t* gh, const lgcn_layer_arg
   p.one_minus_b2 = (float)(1.0 - a->beta2);
   p.eps = (float)a->eps;
   p.zero_base = a->zero_base;
+  p.push_emb = a->push_emb;
+  LGCN_CHECK_ARG(!a->push_emb || (a->grad_mode == 2 && a->dst != nullptr), "push_emb needs grad_mode 2 and dst");
   LGCN_CHECK_ARG(a->n_dst_peers >= 0 && a->n_dst_peers <= LGCN_MAX_PEERS, "n_dst_peers out of range");
   p.n_peer = a->n_dst_peers;
   p.dst_row_off = a->dst_row_offset;

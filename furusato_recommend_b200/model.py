@@ -68,13 +68,15 @@ class _PropagateFn(torch.autograd.Function):
         ctx.model = model
         out = torch.empty_like(weight)
         model._propagate_into(weight.detach(), out)
+        ctx.drop_bwd = model._drop_bwd   # an intervening computer() redraws the mask: keep this pass's
         return out
 
     @staticmethod
     def backward(ctx, grad_out: torch.Tensor):
         m: "LightGCN" = ctx.model
         grad = torch.empty_like(grad_out)
-        m._horner_into(grad_out.contiguous(), grad_mode=1, reg_coef=0.0, grad=grad, cnt=m._zero_cnt())
+        m._horner_into(grad_out.contiguous(), grad_mode=1, reg_coef=0.0, grad=grad, cnt=m._zero_cnt(),
+                       edge_w=ctx.drop_bwd)
         return grad, None
 
 
@@ -93,6 +95,8 @@ class _BprFn(torch.autograd.Function):
         m._g_clean = False
         m._seed_generation += 1
         ctx.model, ctx.gen, ctx.batch = m, m._seed_generation, users.numel()
+        ctx.drop_bwd = m._drop_bwd
+        m._raise_on_bad_ids()   # eager path: one sync, the reference's IndexError (model/lgcn.py:90-95)
         return lo[0].clone(), lo[1].clone()
 
     @staticmethod
@@ -105,7 +109,7 @@ class _BprFn(torch.autograd.Function):
         if gl != 1.0:
             G.mul_(gl)
         grad = torch.empty_like(m.all_embedding.weight)
-        m._horner_into(G, grad_mode=1, reg_coef=gr / ctx.batch, grad=grad, cnt=m._buf("cnt"))
+        m._horner_into(G, grad_mode=1, reg_coef=gr / ctx.batch, grad=grad, cnt=m._buf("cnt"), edge_w=ctx.drop_bwd)
         return grad, None, None, None, None
 
 
@@ -123,7 +127,9 @@ class LightGCN(nn.Module):
             raise NotImplementedError("layer=0 is plain matrix factorisation, outside the LightGCN hot path")
         self.device = torch.device(config.get("device", "cuda:0"))
         self.storage_dtype = _STORAGE[config.get("storage_dtype", "fp32")]
-        self.eval_precision = config.get("eval_precision", "fp32")
+        # full-rank eval scores on the tcgen05 tensor cores by default (bf16 operands, fp32 accumulate,
+        # 2e-2 relative to the fp32 scores, north_star); "fp32" is the exactness mode (CUDA cores)
+        self.eval_precision = config.get("eval_precision", "bf16")
         self.graph: CsrGraph = self._build_graph(dataset)
         if self.graph.device != self.device:
             self.graph = self.graph.to(self.device)
@@ -143,6 +149,7 @@ class LightGCN(nn.Module):
         self._g_clean = True
         self._seed_generation = 0
         self._eval_cache_valid = False
+        self._eval_cache_key = None
         self.use_cuda_graph = bool(config.get("cuda_graph", True))
         self._graph = None
         self._graph_key = None
@@ -202,8 +209,8 @@ class LightGCN(nn.Module):
                 t = torch.zeros(N, dtype=torch.int32, device=dev)
             elif name == "loss_out":
                 t = torch.zeros(4, dtype=torch.float32, device=dev)
-            elif name == "work_counter":
-                t = torch.zeros(1, dtype=torch.int32, device=dev)
+            elif name == "work_counter":   # {CTA arrival counter, skipped out-of-range samples}
+                t = torch.zeros(2, dtype=torch.int32, device=dev)
             else:
                 raise KeyError(name)
             self._bufs[name] = t
@@ -218,6 +225,23 @@ class LightGCN(nn.Module):
 
     def _zero_cnt(self) -> torch.Tensor:
         return self._buf("zero_cnt")
+
+    def _raise_on_bad_ids(self) -> None:
+        """The BPR kernel skips (and counts) samples whose ids fall outside the table instead of
+        scattering out of bounds; surface them as the reference's IndexError.  One host sync."""
+        wc = self._buf("work_counter")
+        bad = int(wc[1].item())
+        if bad:
+            wc[1] = 0
+            raise IndexError(f"{bad} (user, pos, neg) sample(s) with an id outside [0, {self.num_users}) / "
+                             f"[0, {self.num_items}) were skipped (reference: IndexError at model/lgcn.py:90-95)")
+
+    def _check_host_ids(self, users, pos, neg) -> None:
+        """Ids that arrive on the host are range-checked there (cheap), before anything is launched."""
+        for t, hi, nm in ((users, self.num_users, "user"), (pos, self.num_items, "positive item"),
+                          (neg, self.num_items, "negative item")):
+            if torch.is_tensor(t) and not t.is_cuda and t.numel() and (int(t.min()) < 0 or int(t.max()) >= hi):
+                raise IndexError(f"{nm} id out of range [0, {hi})")
 
     def _reset_seed_buffers(self) -> None:
         if not self._g_clean:
@@ -244,12 +268,14 @@ class LightGCN(nn.Module):
                 acc_scale=1.0 / (K + 1) if last else 1.0, edge_w=self._drop_fwd, **self._scales(False))
 
     def _horner_into(self, G: torch.Tensor, *, grad_mode: int, reg_coef: float, cnt: torch.Tensor,
-                     grad: Optional[torch.Tensor] = None, adam: Optional[dict] = None) -> None:
+                     grad: Optional[torch.Tensor] = None, adam: Optional[dict] = None, edge_w="own") -> None:
         """H0 = G, H_{j+1} = G + A_hat H_j; result H_K/(K+1) + reg_coef*cnt*E goes to
         `grad` (mode 1) or straight into Adam (mode 2)  (SURVEY §8 a-3)."""
         K, g = self.num_layers, self.graph
         z = [self._buf("Z0"), self._buf("Z1")]
         w = self.all_embedding.weight.detach()
+        if isinstance(edge_w, str):   # the dropout weights of the latest propagation (fused step)
+            edge_w = self._drop_bwd
         for j in range(K):
             last = j == K - 1
             kw = {}
@@ -260,7 +286,7 @@ class LightGCN(nn.Module):
                     kw.update(adam_m=adam["exp_avg"], adam_v=adam["exp_avg_sq"], adam_hp=adam["hp"],
                               betas=adam["betas"], eps=adam["eps"], zero_base=K > 1)
             ops.propagate_layer(g, G if j == 0 else z[(j - 1) & 1], scale_src=(j == 0),
-                                dst=None if last else z[j & 1], base=G, edge_w=self._drop_bwd, **kw,
+                                dst=None if last else z[j & 1], base=G, edge_w=edge_w, **kw,
                                 **self._scales(True))
 
     def computer(self) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -270,9 +296,15 @@ class LightGCN(nn.Module):
             out = _PropagateFn.apply(w, self)
         else:
             out = self._buf("OUT")
-            if self.training or not self._eval_cache_valid:
+            # The eval-mode cache is keyed on the table's storage and autograd version, so in-place
+            # edits made through torch (`weight.copy_`, optimizer steps on the autograd path,
+            # load_state_dict) invalidate it; the fused kernels write through raw pointers and drop
+            # the flag themselves.
+            key = (w.data_ptr(), w._version)
+            if self.training or not self._eval_cache_valid or self._eval_cache_key != key:
                 self._propagate_into(w.detach(), out)
                 self._eval_cache_valid = not self.training
+                self._eval_cache_key = key
         return out[: self.num_users], out[self.num_users:]
 
     def forward(self) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -304,9 +336,10 @@ class LightGCN(nn.Module):
     def stageOne(self, user, pos, neg) -> torch.Tensor:
         """model/lgcn.py:127-133 as one fused step: zero_grad + bpr_loss +
         decay*reg + backward + Adam.  Returns loss + decay*reg (0-dim tensor)."""
-        self._fused_step(self._ids(user, keep_host=True), self._ids(pos, keep_host=True),
-                         self._ids(neg, keep_host=True))
-        return self._buf("loss_out")[2].clone()
+        u, p, q = self._ids(user, keep_host=True), self._ids(pos, keep_host=True), self._ids(neg, keep_host=True)
+        self._check_host_ids(u, p, q)
+        self._fused_step(u, p, q)
+        return self._buf("loss_out")[2].clone()   # NaN if a device-side id was out of range (see OneEpoch)
 
     def _fused_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> None:
         """One fused train step.  Full-size batches replay a captured CUDA graph (8 kernels, no
@@ -317,7 +350,7 @@ class LightGCN(nn.Module):
             return self._fused_step_eager(self._ids(users), self._ids(pos), self._ids(neg))
         self._reset_seed_buffers()  # only dirty after the autograd path; the graph assumes clean G/cnt
         lr = self.optim.param_groups[0]["lr"]
-        if self._graph is None or self._graph_key != (B, lr, float(self.config["decay"]), self.num_layers):
+        if self._graph is None or self._graph_key != self._step_graph_key(B):
             self._capture_step_graph(B)
         for dst, src in zip(self._gbatch, (users, pos, neg)):
             dst.copy_(src, non_blocking=True)      # device slice or pinned host memory
@@ -343,7 +376,15 @@ class LightGCN(nn.Module):
                          self._buf("loss_out")), keep):
             t.copy_(k)
         self._graph = graph
-        self._graph_key = (B, self.optim.param_groups[0]["lr"], float(self.config["decay"]), self.num_layers)
+        self._graph_key = self._step_graph_key(B)
+
+    def _step_graph_key(self, B: int):
+        """Everything the captured step bakes in: scalars AND the addresses of the table and of the
+        optimizer state (optim.load_state_dict replaces exp_avg / exp_avg_sq)."""
+        st = self.optim._init_state(self.all_embedding.weight)
+        return (B, self.optim.param_groups[0]["lr"], float(self.config["decay"]), self.num_layers,
+                self.all_embedding.weight.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                st["step"].data_ptr(), st["hp"].data_ptr())
 
     def _fused_step_eager(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> None:
         w = self.all_embedding.weight
@@ -376,6 +417,7 @@ class LightGCN(nn.Module):
         lo[3] = 0.0
         for i in range(0, len(users), B):
             self._fused_step(users[i:i + B], pos[i:i + B], neg[i:i + B])
+        self._raise_on_bad_ids()   # one sync per epoch
         return lo[3] / total_batch
 
     # -------------------------------------------------------------------- eval

@@ -15,8 +15,26 @@ from .graph import CsrGraph
 MASK_VALUE = -float(1 << 10)  # reference trainer.py:137
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+class _on:
+    """Device guard + stream of one op: the launch goes to the device that holds the tensors (not to
+    whatever device happens to be current — `config['device']='cuda:1'` works like in the reference)
+    and to torch's current stream on THAT device.  Tensors on mixed devices are rejected."""
+
+    def __init__(self, *tensors):
+        devs = {t.device for t in tensors if torch.is_tensor(t)}
+        if any(dv.type != "cuda" for dv in devs):
+            raise _lib.LgcnLibraryError("CUDA tensors required: the LightGCN hot path has no CPU fallback")
+        if len(devs) != 1:
+            raise ValueError(f"all tensors of one op must live on one CUDA device, got {sorted(map(str, devs))}")
+        self.device = devs.pop()
+        self._guard = torch.cuda.device(self.device)
+
+    def __enter__(self) -> int:
+        self._guard.__enter__()
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def __exit__(self, *exc):
+        return self._guard.__exit__(*exc)
 
 
 def _chk(t: Optional[torch.Tensor], dtype, name: str, allow_none: bool = False) -> int:
@@ -51,7 +69,7 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
                     betas=(0.9, 0.999), eps: float = 1e-8, zero_base: bool = False,
                     dst_peers: Optional[Sequence[int]] = None, dst_row_offset: int = 0,
                     src_scale: Optional[torch.Tensor] = None, dst_scale: Optional[torch.Tensor] = None,
-                    edge_w: Optional[torch.Tensor] = None) -> None:
+                    edge_w: Optional[torch.Tensor] = None, push_emb: bool = False) -> None:
     """lgcn_propagate_layer: one normalised-adjacency SpMM + fused row epilogue.
     `src_scale` / `dst_scale` ([N] fp32) replace the graph's dinv on the column / row side
     (rAdjGCN's asymmetric normalisation); None keeps D^-1/2 A D^-1/2.  `edge_w` ([nnz] fp32) weights
@@ -79,6 +97,7 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
     a.adam_hp = _chk(adam_hp, torch.float32, "adam_hp", True)
     a.beta1, a.beta2, a.eps = betas[0], betas[1], eps
     a.zero_base = int(zero_base)
+    a.push_emb = int(push_emb)
     for t, nm in ((src_scale, "src_scale"), (dst_scale, "dst_scale")):
         if t is not None and (t.dim() != 1 or t.shape[0] < N):
             raise ValueError(f"{nm} must be [>={N}], got {tuple(t.shape)}")
@@ -97,7 +116,8 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
                   (grad, "grad"), (adam_m, "adam_m"), (adam_v, "adam_v")):
         if t is not None and (t.dim() != 2 or t.shape[0] < N or t.shape[1] != d):
             raise ValueError(f"{nm} must be [>={N}, {d}], got {tuple(t.shape)}")
-    _lib.check(lib.lgcn_propagate_layer(C.byref(g.c_struct(d)), C.byref(a), _stream()), "lgcn_propagate_layer")
+    with _on(src, dst, base, acc_in, acc_out, emb, grad, adam_m, adam_v, g.col) as st:
+        _lib.check(lib.lgcn_propagate_layer(C.byref(g.c_struct(d)), C.byref(a), st), "lgcn_propagate_layer")
 
 
 def scale_rows_push(x: torch.Tensor, dinv: torch.Tensor, dst_dtype: torch.dtype, dst_peers: Sequence[int],
@@ -106,9 +126,10 @@ def scale_rows_push(x: torch.Tensor, dinv: torch.Tensor, dst_dtype: torch.dtype,
     lib = _lib.load()
     n, d = x.shape
     arr = (C.c_void_p * len(dst_peers))(*dst_peers)
-    _lib.check(lib.lgcn_scale_rows_push(_chk(x, torch.float32, "x"), _chk(dinv, torch.float32, "dinv"), n, d,
-                                        _lib.BF16 if dst_dtype == torch.bfloat16 else _lib.F32, arr, len(dst_peers),
-                                        dst_row_offset, _stream()), "lgcn_scale_rows_push")
+    with _on(x, dinv) as st:
+        _lib.check(lib.lgcn_scale_rows_push(_chk(x, torch.float32, "x"), _chk(dinv, torch.float32, "dinv"), n, d,
+                                            _lib.BF16 if dst_dtype == torch.bfloat16 else _lib.F32, arr, len(dst_peers),
+                                            dst_row_offset, st), "lgcn_scale_rows_push")
 
 
 def exchange_rows_push(tab_a: torch.Tensor, tab_b: Optional[torch.Tensor], padded_ids: torch.Tensor,
@@ -117,10 +138,11 @@ def exchange_rows_push(tab_a: torch.Tensor, tab_b: Optional[torch.Tensor], padde
     lib = _lib.load()
     d = tab_a.shape[1]
     arr = (C.c_void_p * len(dst_peers))(*dst_peers)
-    _lib.check(lib.lgcn_exchange_rows_push(_chk(tab_a, torch.float32, "tab_a"), _chk(tab_b, torch.float32, "tab_b", True),
-                                           d, _chk(padded_ids, torch.int64, "padded_ids"), padded_ids.numel(),
-                                           rows_per_rank, rank, arr, len(dst_peers), _stream()),
-               "lgcn_exchange_rows_push")
+    with _on(tab_a, tab_b, padded_ids) as st:
+        _lib.check(lib.lgcn_exchange_rows_push(_chk(tab_a, torch.float32, "tab_a"), _chk(tab_b, torch.float32, "tab_b", True),
+                                               d, _chk(padded_ids, torch.int64, "padded_ids"), padded_ids.numel(),
+                                               rows_per_rank, rank, arr, len(dst_peers), st),
+                   "lgcn_exchange_rows_push")
 
 
 def bpr_fwd_bwd(out: torch.Tensor, emb: torch.Tensor, users: torch.Tensor, pos: torch.Tensor,
@@ -132,27 +154,75 @@ def bpr_fwd_bwd(out: torch.Tensor, emb: torch.Tensor, users: torch.Tensor, pos: 
     N, d = out.shape
     if work.numel() < 2 * B:
         raise ValueError("work must hold 2*B floats")
-    _lib.check(lib.lgcn_bpr_fwd_bwd(
-        _chk(out, torch.float32, "out"), _chk(emb, torch.float32, "emb"),
-        _chk(users, torch.int64, "users"), _chk(pos, torch.int64, "pos"), _chk(neg, torch.int64, "neg"),
-        B, n_users, N, d, decay, loss_scale, _chk(G, torch.float32, "G"), _chk(cnt, torch.int32, "cnt"),
-        _chk(loss_out, torch.float32, "loss_out"), _chk(work, torch.float32, "work"),
-        _chk(work_counter, torch.int32, "work_counter"), _stream()), "lgcn_bpr_fwd_bwd")
+    if work_counter.numel() < 2:
+        raise ValueError("work_counter must be int32[2]: {CTA arrival counter, skipped out-of-range samples}")
+    with _on(out, emb, users, pos, neg, G, cnt, loss_out, work, work_counter) as st:
+        _lib.check(lib.lgcn_bpr_fwd_bwd(
+            _chk(out, torch.float32, "out"), _chk(emb, torch.float32, "emb"),
+            _chk(users, torch.int64, "users"), _chk(pos, torch.int64, "pos"), _chk(neg, torch.int64, "neg"),
+            B, n_users, N, d, decay, loss_scale, _chk(G, torch.float32, "G"), _chk(cnt, torch.int32, "cnt"),
+            _chk(loss_out, torch.float32, "loss_out"), _chk(work, torch.float32, "work"),
+            _chk(work_counter, torch.int32, "work_counter"), st), "lgcn_bpr_fwd_bwd")
+
+
+def padded_ids(users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, n_users: int, n_nodes: int,
+               cuts: torch.Tensor, side_off: torch.Tensor, world: int, rows_per_rank: int, out: torch.Tensor,
+               status: torch.Tensor) -> None:
+    """out[3B] = padded partition ids of [users | n+pos | n+neg] (lgcn_padded_ids)."""
+    lib = _lib.load()
+    B = users.numel()
+    if out.numel() < 3 * B:
+        raise ValueError("out must hold 3*B ids")
+    with _on(users, pos, neg, cuts, side_off, out, status) as st:
+        _lib.check(lib.lgcn_padded_ids(_chk(users, torch.int64, "users"), _chk(pos, torch.int64, "pos"),
+                                       _chk(neg, torch.int64, "neg"), B, n_users, n_nodes,
+                                       _chk(cuts, torch.int64, "cuts"), _chk(side_off, torch.int64, "side_off"), world,
+                                       rows_per_rank, _chk(out, torch.int64, "out"), status.data_ptr(), st),
+                   "lgcn_padded_ids")
+
+
+def bpr_fwd_bwd_rows(rows: torch.Tensor, ids: torch.Tensor, batch: int, rows_per_rank: int, rank: int, decay: float,
+                     G: torch.Tensor, cnt: torch.Tensor, g0_full: Optional[torch.Tensor],
+                     dinv_pad: Optional[torch.Tensor], loss_out: torch.Tensor, work: torch.Tensor,
+                     work_counter: torch.Tensor, loss_scale: float = 1.0) -> None:
+    """lgcn_bpr_fwd_bwd_rows: BPR on the owner-filled compact table rows[3B, 2d]."""
+    lib = _lib.load()
+    d = G.shape[1]
+    if rows.dim() != 2 or rows.shape[1] != 2 * d or rows.shape[0] < 3 * batch or ids.numel() < 3 * batch:
+        raise ValueError("rows must be [>=3B, 2d] and ids [>=3B]")
+    if work.numel() < 2 * batch or work_counter.numel() < 2:
+        raise ValueError("work must hold 2*B floats, work_counter 2 ints")
+    with _on(rows, ids, G, cnt, g0_full, dinv_pad, loss_out, work, work_counter) as st:
+        _lib.check(lib.lgcn_bpr_fwd_bwd_rows(
+            _chk(rows, torch.float32, "rows"), _chk(ids, torch.int64, "ids"), batch, d, rows_per_rank, rank, decay,
+            loss_scale, _chk(G, torch.float32, "G"), _chk(cnt, torch.int32, "cnt"),
+            _chk(g0_full, torch.float32, "g0_full", True), _chk(dinv_pad, torch.float32, "dinv_pad", True),
+            _chk(loss_out, torch.float32, "loss_out"), _chk(work, torch.float32, "work"),
+            _chk(work_counter, torch.int32, "work_counter"), st), "lgcn_bpr_fwd_bwd_rows")
+
+
+def zero_rows(table: torch.Tensor, ids: torch.Tensor) -> None:
+    lib = _lib.load()
+    with _on(table, ids) as st:
+        _lib.check(lib.lgcn_zero_rows(_chk(table, torch.float32, "table"), table.shape[1],
+                                      _chk(ids, torch.int64, "ids"), ids.numel(), st), "lgcn_zero_rows")
 
 
 def adam_tick(step: torch.Tensor, hp: torch.Tensor, lr: float, betas=(0.9, 0.999)) -> None:
     lib = _lib.load()
-    _lib.check(lib.lgcn_adam_tick(_chk(step, torch.int64, "step"), _chk(hp, torch.float32, "adam_hp"),
-                                  lr, betas[0], betas[1], _stream()), "lgcn_adam_tick")
+    with _on(step, hp) as st:
+        _lib.check(lib.lgcn_adam_tick(_chk(step, torch.int64, "step"), _chk(hp, torch.float32, "adam_hp"),
+                                      lr, betas[0], betas[1], st), "lgcn_adam_tick")
 
 
 def adam_step(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, hp: torch.Tensor,
               betas=(0.9, 0.999), eps: float = 1e-8) -> None:
     lib = _lib.load()
-    _lib.check(lib.lgcn_adam_step(_chk(param, torch.float32, "param"), _chk(grad, torch.float32, "grad"),
-                                  _chk(m, torch.float32, "m"), _chk(v, torch.float32, "v"), param.numel(),
-                                  _chk(hp, torch.float32, "adam_hp"), betas[0], betas[1], eps, _stream()),
-               "lgcn_adam_step")
+    with _on(param, grad, m, v, hp) as st:
+        _lib.check(lib.lgcn_adam_step(_chk(param, torch.float32, "param"), _chk(grad, torch.float32, "grad"),
+                                      _chk(m, torch.float32, "m"), _chk(v, torch.float32, "v"), param.numel(),
+                                      _chk(hp, torch.float32, "adam_hp"), betas[0], betas[1], eps, st),
+                   "lgcn_adam_step")
 
 
 def uniform_sample(pos_rowptr: torch.Tensor, pos_file: torch.Tensor, pos_sorted: torch.Tensor,
@@ -167,12 +237,13 @@ def uniform_sample(pos_rowptr: torch.Tensor, pos_file: torch.Tensor, pos_sorted:
     valid = torch.empty(count * n_neg, dtype=torch.uint8, device=dev)
     if pos_cdf is not None and pos_cdf.numel() != pos_file.numel():
         raise ValueError("pos_cdf must align with pos_file")
-    _lib.check(lib.lgcn_uniform_sample_weighted(
-        _chk(pos_rowptr, torch.int64, "pos_rowptr"), _chk(pos_file, torch.int32, "pos_file"),
-        _chk(pos_sorted, torch.int32, "pos_sorted"), _chk(pos_cdf, torch.float32, "pos_cdf", True),
-        n_users, m_items, first, count, n_neg,
-        seed & 0xFFFFFFFFFFFFFFFF, epoch & 0xFFFFFFFF, triples.data_ptr(), valid.data_ptr(), _stream()),
-        "lgcn_uniform_sample_weighted")
+    with _on(pos_rowptr, pos_file, pos_sorted, pos_cdf) as st:
+        _lib.check(lib.lgcn_uniform_sample_weighted(
+            _chk(pos_rowptr, torch.int64, "pos_rowptr"), _chk(pos_file, torch.int32, "pos_file"),
+            _chk(pos_sorted, torch.int32, "pos_sorted"), _chk(pos_cdf, torch.float32, "pos_cdf", True),
+            n_users, m_items, first, count, n_neg,
+            seed & 0xFFFFFFFFFFFFFFFF, epoch & 0xFFFFFFFF, triples.data_ptr(), valid.data_ptr(), st),
+            "lgcn_uniform_sample_weighted")
     return triples, valid
 
 
@@ -184,9 +255,10 @@ def compact_triples(triples: torch.Tensor, valid: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(triples)
     n_out = torch.zeros(1, dtype=torch.int64, device=dev)
     scratch = torch.empty((count + 1023) // 1024 + 1, dtype=torch.int64, device=dev)
-    _lib.check(lib.lgcn_compact_triples(_chk(triples, torch.int64, "triples"), _chk(valid, torch.uint8, "valid"),
-                                        count, out.data_ptr(), n_out.data_ptr(), scratch.data_ptr(), _stream()),
-               "lgcn_compact_triples")
+    with _on(triples, valid) as st:
+        _lib.check(lib.lgcn_compact_triples(_chk(triples, torch.int64, "triples"), _chk(valid, torch.uint8, "valid"),
+                                            count, out.data_ptr(), n_out.data_ptr(), scratch.data_ptr(), st),
+                   "lgcn_compact_triples")
     return out[: int(n_out.item())]
 
 
@@ -220,11 +292,12 @@ def score_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, user_ids: torch.T
             _chk(user_ids, torch.int64, "user_ids"), U, m, d, _chk(pos_rowptr, torch.int64, "pos_rowptr"),
             _chk(pos_sorted, torch.int32, "pos_sorted"), k, mask_value, prec, idx.data_ptr(), val.data_ptr(),
             ws.data_ptr() if ws is not None else 0, nbytes]
-    if return_scores:
-        dense = torch.empty((U, m), dtype=torch.float32, device=dev)
-        _lib.check(lib.lgcn_score_topk_debug(*args, dense.data_ptr(), _stream()), "lgcn_score_topk_debug")
-        return idx, val, dense
-    _lib.check(lib.lgcn_score_topk(*args, _stream()), "lgcn_score_topk")
+    with _on(user_emb, item_emb, user_ids, pos_rowptr, pos_sorted) as st:
+        if return_scores:
+            dense = torch.empty((U, m), dtype=torch.float32, device=dev)
+            _lib.check(lib.lgcn_score_topk_debug(*args, dense.data_ptr(), st), "lgcn_score_topk_debug")
+            return idx, val, dense
+        _lib.check(lib.lgcn_score_topk(*args, st), "lgcn_score_topk")
     return idx, val
 
 
@@ -233,10 +306,11 @@ def score_dense_f32(user_emb: torch.Tensor, item_emb: torch.Tensor, user_ids: to
     U = user_ids.numel()
     m, d = item_emb.shape
     out = torch.empty((U, m), dtype=torch.float32, device=item_emb.device)
-    _lib.check(lib.lgcn_score_dense_f32(_chk(user_emb, torch.float32, "user_emb"),
-                                        _chk(item_emb, torch.float32, "item_emb"),
-                                        _chk(user_ids, torch.int64, "user_ids"), U, m, d, out.data_ptr(),
-                                        _stream()), "lgcn_score_dense_f32")
+    with _on(user_emb, item_emb, user_ids) as st:
+        _lib.check(lib.lgcn_score_dense_f32(_chk(user_emb, torch.float32, "user_emb"),
+                                            _chk(item_emb, torch.float32, "item_emb"),
+                                            _chk(user_ids, torch.int64, "user_ids"), U, m, d, out.data_ptr(),
+                                            st), "lgcn_score_dense_f32")
     return out
 
 
@@ -253,11 +327,12 @@ def rank_metrics(topk: torch.Tensor, user_ids: torch.Tensor, test_rowptr: torch.
     tmp = torch.zeros((4, len(ks)), dtype=torch.float64, device=dev)
     hits = torch.empty((U, k), dtype=torch.uint8, device=dev) if want_hits else None
     arr = (C.c_int32 * len(ks))(*ks_sorted)
-    _lib.check(lib.lgcn_rank_metrics(_chk(topk, torch.int32, "topk"), U, k, _chk(user_ids, torch.int64, "user_ids"),
-                                     _chk(test_rowptr, torch.int64, "test_rowptr"),
-                                     _chk(test_sorted, torch.int32, "test_sorted"), arr, len(ks),
-                                     tmp.data_ptr(), hits.data_ptr() if hits is not None else 0, _stream()),
-               "lgcn_rank_metrics")
+    with _on(topk, user_ids, test_rowptr, test_sorted) as st:
+        _lib.check(lib.lgcn_rank_metrics(_chk(topk, torch.int32, "topk"), U, k, _chk(user_ids, torch.int64, "user_ids"),
+                                         _chk(test_rowptr, torch.int64, "test_rowptr"),
+                                         _chk(test_sorted, torch.int32, "test_sorted"), arr, len(ks),
+                                         tmp.data_ptr(), hits.data_ptr() if hits is not None else 0, st),
+                   "lgcn_rank_metrics")
     inv = torch.empty(len(ks), dtype=torch.long)
     for pos_sorted_i, orig_i in enumerate(order):
         inv[orig_i] = pos_sorted_i

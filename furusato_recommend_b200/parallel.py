@@ -229,14 +229,21 @@ class DistPropagator:
 
 
 class PushPropagator:
-    """Same maths as DistPropagator, but the per-layer all-gather is FUSED into the producing
-    kernel: the SpMM epilogue stores every pre-scaled output row straight into all ranks'
-    gathered buffers through NVLink peer mappings (torch symmetric memory supplies the mapped
-    pointers and the cross-GPU barrier).  No NCCL call and no staging copy on the layer path;
-    the transfer overlaps the gather/FMA work of the same kernel row by row.
+    """Same maths as DistPropagator, but every per-layer all-gather is FUSED into the producing
+    kernel: the SpMM epilogue stores each pre-scaled output row straight into the gathered buffers
+    of the ranks that read it, through NVLink peer mappings (torch symmetric memory supplies the
+    mapped pointers and the cross-GPU barrier).  No NCCL call and no staging copy on the layer
+    path; the transfer overlaps the gather/FMA work of the same kernel row by row.
 
-    Two symmetric [W*R, d] buffers ping-pong: layer k reads buf[k&1] and pushes into buf[(k+1)&1]
-    of every peer; one barrier per layer separates the writers of a buffer from its readers."""
+    Exchanges per train step: 2K - 1, all fused.
+      * forward layer k reads buf[k & 1] and pushes X_{k+1} into buf[(k + 1) & 1] of its readers;
+      * the backward pass needs no exchange for its first layer: the gradient seed has <= 3B
+        non-zero rows that every rank already holds (the compact BPR table), so its pre-scaled
+        gathered copy `g0` is built locally by lgcn_bpr_fwd_bwd_rows;
+      * the LAST backward layer's Adam epilogue pushes dinv (.) E_new — the next step's layer-0
+        source — into buf[0] (`push_emb`), so the updated table is never exchanged separately.
+    One barrier separates the writers of a buffer from its readers: K + 1 per pass pair
+    (start of forward, after every non-final layer)."""
 
     def __init__(self, part: RowPartition, rank: int, graph, dinv_local: torch.Tensor, n_layers: int,
                  ops, group, d: int, storage_dtype: torch.dtype, device):
@@ -251,39 +258,54 @@ class PushPropagator:
         readers = part.readers_of(rank)   # side-split partition: only the other side's ranks
         self.peers = [[int(h.buffer_ptrs[r]) for r in readers] for h in self.hdl]
         self.row0 = rank * R
+        self.x0_valid = False   # buf[0] holds dinv (.) E of the CURRENT table on every reader
 
     def _barrier(self):
         self.hdl[0].barrier(channel=0)
 
-    def _run(self, first_src: torch.Tensor, layer_kwargs, g0=None):
+    def push_x0(self, emb_local: torch.Tensor) -> None:
+        """Explicit exchange of the pre-scaled table (first step, after load_global_embedding, after
+        an eval-only propagation): every later train step gets it from the Adam epilogue."""
+        self._barrier()  # every peer is done reading buf[0]
+        self.ops.scale_rows_push(emb_local, self.dinv, self.storage_dtype, self.peers[0], self.row0)
+        self.x0_valid = True
+
+    def forward(self, emb_local: torch.Tensor, acc: torch.Tensor, out: torch.Tensor) -> None:
         ops, K = self.ops, self.K
-        if g0 is not None:
-            # Backward pass with a sparse seed: the layer-0 source is built in this rank's OWN buffer, no
-            # exchange.  The caller guarantees a cross-GPU barrier between the previous pass and this one
-            # (the BPR row exchange has one), so no peer still reads the buffer layer 0 pushes into.
-            build_g0(self.bufs[0], *g0)
-        else:
-            self._barrier()  # every peer is done reading buf[0] (last layer of the previous pass)
-            ops.scale_rows_push(first_src, self.dinv, self.storage_dtype, self.peers[0], self.row0)
-            self._barrier()
+        if not self.x0_valid:
+            self.push_x0(emb_local)
+        self._barrier()  # the X0 rows (previous step's Adam epilogue, or push_x0) are visible everywhere
         for k in range(K):
             last = k == K - 1
             nxt = (k + 1) & 1
             ops.propagate_layer(self.graph, self.bufs[k & 1], scale_src=False,
                                 dst=None if last else self.bufs[nxt],
                                 dst_peers=None if last else self.peers[nxt], dst_row_offset=self.row0,
-                                **layer_kwargs(k, last))
+                                acc_in=emb_local if k == 0 else acc, acc_out=out if last else acc,
+                                acc_scale=1.0 / (K + 1) if last else 1.0)
             if not last:
                 self._barrier()
+        if K > 1:
+            self.x0_valid = False   # layer 1 pushed X2 over X0
 
-    def forward(self, emb_local: torch.Tensor, acc: torch.Tensor, out: torch.Tensor) -> None:
-        K = self.K
-        self._run(emb_local, lambda k, last: dict(
-            acc_in=emb_local if k == 0 else acc, acc_out=out if last else acc,
-            acc_scale=1.0 / (K + 1) if last else 1.0))
-
-    def backward(self, G_local: torch.Tensor, g0=None, **last_kwargs) -> None:
-        self._run(G_local, lambda k, last: dict(base=G_local, **(last_kwargs if last else {})), g0=g0)
+    def backward(self, G_local: torch.Tensor, g0_src: torch.Tensor, **last_kwargs) -> None:
+        """H0 = G, H_{j+1} = G + A_hat H_j.  `g0_src` fp32 [W*R, d] = dinv (.) G in the padded layout
+        (local).  Layer j reads buf[(a + j) & 1] (j > 0) and pushes into buf[(a + j + 1) & 1] with
+        a = K & 1, so the last layer's push — the updated, pre-scaled table — lands in buf[0].  The
+        caller guarantees a cross-GPU barrier between the forward pass and this call (the BPR row
+        exchange has one), so no peer still reads the buffer layer 0 pushes into."""
+        ops, K = self.ops, self.K
+        a = K & 1
+        for j in range(K):
+            last = j == K - 1
+            nxt = (a + j + 1) & 1
+            kw = dict(last_kwargs, push_emb=True) if last else {}
+            ops.propagate_layer(self.graph, g0_src if j == 0 else self.bufs[(a + j) & 1], scale_src=False,
+                                dst=self.bufs[nxt], dst_peers=self.peers[nxt], dst_row_offset=self.row0,
+                                base=G_local, **kw)
+            if not last:
+                self._barrier()
+        self.x0_valid = True
 
 
 def exchange_rows(part: RowPartition, rank: int, local, padded_ids: torch.Tensor, group=None):
@@ -336,7 +358,7 @@ class DistLightGCN:
         self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
         self.hp = torch.zeros(2, dtype=torch.float32, device=dev)
         self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)
-        self.work_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.work_counter = torch.zeros(2, dtype=torch.int32, device=dev)
         storage = torch.bfloat16 if config.get("storage_dtype") == "bf16" else torch.float32
         # "push": all-gather fused into the SpMM epilogue over NVLink peer memory (default when the
         # ranks can map each other's memory); "nccl": ncclAllGather per layer (the baseline).
@@ -356,14 +378,21 @@ class DistLightGCN:
         if self.prop is None:
             self.prop = DistPropagator(self.part, rank, dl, self.K, self._local_spmm, group, storage)
         self.collectives_per_step = 2 * self.K + 1
-        # EXPERIMENTAL (default off, CPU-tested index logic only): build the backward pass's layer-0 source
-        # locally from the compact BPR table instead of exchanging the G shards (fp32 storage only)
-        self.sparse_g0 = bool(config.get("dist_sparse_g0", False)) and storage == torch.float32 and world > 1
+        # NCCL baseline only (CPU-tested index logic): build the backward pass's layer-0 source locally
+        # from the compact BPR table instead of all-gathering the G shards (fp32 storage only).  The
+        # push exchange always does this, in its BPR kernel.
+        self.sparse_g0 = (bool(config.get("dist_sparse_g0", False)) and storage == torch.float32 and world > 1
+                          and self.exchange == "nccl")
         self._dinv_pad = None
-        if self.sparse_g0:
+        if self.sparse_g0 or self.exchange == "push":
             self._dinv_pad = torch.zeros(world * R, dtype=torch.float32, device=dev)
             self._dinv_pad[self.part.to_padded(torch.arange(self.n + self.m, device=dev))] = g.dinv
-        self._ar = None
+        if self.exchange == "push":
+            # partition tables of lgcn_padded_ids and the local, pre-scaled gradient seed dinv (.) G
+            self._cuts = torch.stack([c.to(torch.int64) for c in self.part.cuts]).contiguous()
+            self._side_off = torch.stack([o.to(torch.int64) for o in self.part.side_off[:2]]).contiguous()
+            self._g0 = torch.zeros((world * R, d), dtype=torch.float32, device=dev)
+        self._cap = 0           # batch size the scratch below was allocated for (grow-only)
         self._xbuf = None
         # Capturing NCCL collectives into a CUDA graph deadlocked on the 2-GPU box (round 1), so the
         # NCCL exchange stays eager unless asked.  The push exchange has no NCCL call on the step at
@@ -371,10 +400,13 @@ class DistLightGCN:
         # which are plain kernels), so its step is captured by default.
         self.use_cuda_graph = bool(config.get("dist_cuda_graph", self.exchange == "push"))
         self._graph = None
+        self._graph_cap = 0
 
     def load_global_embedding(self, E: torch.Tensor) -> None:
         """Take this rank's rows of a global [N, d] table (checkpoint key all_embedding.weight)."""
         self.emb.copy_(self.part.shard(self.rank, E.to(self.device)))
+        if self.exchange == "push":
+            self.prop.x0_valid = False
 
     def gather_embedding(self) -> torch.Tensor:
         full = torch.empty((self.world * self.part.R, self.d), dtype=torch.float32, device=self.device)
@@ -393,20 +425,51 @@ class DistLightGCN:
 
     def fused_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
         """One training step on the same B triples on every rank (global ids).  Full-size batches
-        replay a CUDA graph that holds the kernels, the glue ops AND the NCCL collectives."""
+        replay one CUDA graph (push exchange: kernels and symmetric-memory barriers only); anything
+        else — the last, partial batch of an epoch — runs the same kernels eagerly on the SAME
+        grow-only scratch, so the captured graph never sees a dangling pointer."""
         B = users.numel()
         if not self.use_cuda_graph or B != int(self.config["bpr_batch_size"]):
             users, pos, neg = (t.to(self.device, non_blocking=True) for t in (users, pos, neg))
             return self._fused_step_eager(users, pos, neg)
-        if self._graph is None:
+        if self._graph is None or self._graph_cap != self._cap or self._cap < B:
             self._capture(B)
+        if self.exchange == "push" and not self.prop.x0_valid:
+            self.prop.push_x0(self.emb)   # an eval propagation (or a restore) ran since the last step
         for dst, src in zip(self._gbatch, (users, pos, neg)):
             dst.copy_(src, non_blocking=True)
         self._graph.replay()
+        if self.exchange == "push":
+            self.prop.x0_valid = True
         return self.loss_out[2]
+
+    def _ensure_scratch(self, B: int) -> None:
+        """Per-step scratch, allocated once for the largest batch seen (normally bpr_batch_size) and
+        sliced for smaller ones.  Growing re-allocates (and re-rendezvouses the symmetric exchange
+        buffer on every rank: all ranks see the same batch sizes) and invalidates the graph."""
+        if B <= self._cap:
+            return
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("step scratch must exist before graph capture")
+        cap = max(B, int(self.config["bpr_batch_size"]))
+        dev, d = self.device, self.d
+        self._work = torch.empty(2 * cap, dtype=torch.float32, device=dev)
+        self._ids = torch.zeros(3 * cap, dtype=torch.int64, device=dev)
+        if self.exchange == "push":
+            import torch.distributed._symmetric_memory as symm
+            self._xbuf = symm.empty((3 * cap, 2 * d), dtype=torch.float32, device=dev)
+            self._xhdl = symm.rendezvous(self._xbuf, self.group if self.group is not None else dist.group.WORLD)
+            self._xpeers = [int(p) for p in self._xhdl.buffer_ptrs]
+        else:
+            self._ar = torch.arange(cap, device=dev, dtype=torch.int64)
+            self._G_c = torch.empty((3 * cap, d), dtype=torch.float32, device=dev)
+            self._cnt_c = torch.empty(3 * cap, dtype=torch.int32, device=dev)
+        self._cap = cap
+        self._graph = None
 
     def _capture(self, B: int) -> None:
         dev = self.device
+        self._ensure_scratch(B)
         self._gbatch = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(3)]
         state = (self.emb, self.m1, self.v1, self.step_t, self.hp, self.loss_out)
         keep = [t.clone() for t in state]
@@ -422,25 +485,48 @@ class DistLightGCN:
             self._fused_step_eager(*self._gbatch)
         for t, k in zip(state, keep):
             t.copy_(k)
+        if self.exchange == "push":
+            self.prop.x0_valid = False   # buf[0] holds the warm-up steps' table, not the restored one
         self._graph = graph
+        self._graph_cap = self._cap
 
     def _fused_step_eager(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+        if self.exchange == "push":
+            return self._step_push(users, pos, neg)
+        return self._step_nccl(users, pos, neg)
+
+    def _step_push(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+        """2K SpMM launches (2K - 1 of them carry a fused exchange) + id mapping + row exchange + BPR +
+        Adam tick + row clear; K + 2 ... barriers.  No torch op touches the data path."""
         ops, part, B = self.ops, self.part, users.numel()
+        self._ensure_scratch(B)
+        self.prop.forward(self.emb, self.acc, self.out)
+        ids = self._ids[:3 * B]
+        ops.padded_ids(users, pos, neg, self.n, self.n + self.m, self._cuts, self._side_off, self.world, part.R, ids,
+                       self.work_counter[1:])
+        # owners store [out | emb] rows straight into every rank's [3B, 2d] buffer over NVLink.  No barrier is
+        # needed BEFORE the stores: a peer can only be here after the barriers of this step's forward pass,
+        # which every rank enters after it finished reading the previous step's rows.
+        ops.exchange_rows_push(self.out, self.emb, ids, part.R, self.rank, self._xpeers)
+        self._xhdl.barrier(channel=1)
+        decay = float(self.config["decay"])
+        ops.bpr_fwd_bwd_rows(self._xbuf, ids, B, part.R, self.rank, decay, self.G, self.cnt, self._g0, self._dinv_pad,
+                             self.loss_out, self._work, self.work_counter)
+        ops.adam_tick(self.step_t, self.hp, float(self.config["lr"]))
+        self.prop.backward(self.G, self._g0, grad_mode=2, inv_layers=1.0 / (self.K + 1), reg_coef=decay / B,
+                           cnt=self.cnt, emb=self.emb, adam_m=self.m1, adam_v=self.v1, adam_hp=self.hp, zero_base=True)
+        ops.zero_rows(self._g0, ids)
+        return self.loss_out[2]
+
+    def _step_nccl(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+        """The baseline: ncclAllGather per layer, one [3B, 2d] all-reduce, torch glue."""
+        ops, part, B = self.ops, self.part, users.numel()
+        self._ensure_scratch(B)
         self.prop.forward(self.emb, self.acc, self.out)
         ids = part.to_padded(torch.cat([users, pos + self.n, neg + self.n]))
-        if self.exchange == "push":
-            # owners store [out | emb] rows straight into every rank's [3B, 2d] buffer over NVLink
-            both, mine = self._exchange_rows_push(ids)
-        else:
-            # one all-reduce for both the propagated and the ego rows: [3B, 2d]
-            both, mine = exchange_rows(part, self.rank, [self.out, self.emb], ids, self.group)
+        both, mine = exchange_rows(part, self.rank, [self.out, self.emb], ids, self.group)
         out_c, emb_c = both[:, :self.d].contiguous(), both[:, self.d:].contiguous()
-        if self._ar is None or self._ar.numel() != B:
-            self._ar = torch.arange(B, device=self.device, dtype=torch.int64)
-            self._G_c = torch.empty((3 * B, self.d), dtype=torch.float32, device=self.device)
-            self._cnt_c = torch.empty(3 * B, dtype=torch.int32, device=self.device)
-            self._work = torch.empty(2 * B, dtype=torch.float32, device=self.device)
-        ar, G_c, cnt_c = self._ar, self._G_c, self._cnt_c
+        ar, G_c, cnt_c = self._ar[:B], self._G_c[:3 * B], self._cnt_c[:3 * B]
         G_c.zero_()
         cnt_c.zero_()
         decay = float(self.config["decay"])
@@ -456,23 +542,13 @@ class DistLightGCN:
         self.G.zero_()
         return self.loss_out[2]
 
-    def _exchange_rows_push(self, ids: torch.Tensor):
-        """(rows [3B, 2d], mine [3B]) with the rows written by their owners through peer mappings.
-        No barrier is needed BEFORE the stores: a peer can only be here after the barriers of this
-        step's forward pass, which every rank enters after it finished reading the previous step's
-        rows.  One barrier after the stores publishes them."""
-        import torch.distributed._symmetric_memory as symm
-        n_ids = ids.numel()
-        if self._xbuf is None or self._xbuf.shape[0] != n_ids:
-            if torch.cuda.is_current_stream_capturing():
-                raise RuntimeError("exchange buffer must exist before graph capture")
-            self._xbuf = symm.empty((n_ids, 2 * self.d), dtype=torch.float32, device=self.device)
-            self._xhdl = symm.rendezvous(self._xbuf, self.group if self.group is not None else dist.group.WORLD)
-            self._xpeers = [int(p) for p in self._xhdl.buffer_ptrs]
-        self.ops.exchange_rows_push(self.out, self.emb, ids, self.part.R, self.rank, self._xpeers)
-        self._xhdl.barrier(channel=1)
-        mine = torch.div(ids, self.part.R, rounding_mode="floor") == self.rank
-        return self._xbuf, mine
+    def check_ids(self) -> None:
+        """Raise the reference's IndexError if a step since the last call saw an id outside the table
+        (one host sync; the kernels count and skip them)."""
+        bad = int(self.work_counter[1].item())
+        if bad:
+            self.work_counter[1] = 0
+            raise IndexError(f"{bad} (user, pos, neg) id(s) outside [0, {self.n}) / [0, {self.m})")
 
     def gather_out(self) -> torch.Tensor:
         """Global light_out [N, d] on every rank (eval: the item table is replicated)."""

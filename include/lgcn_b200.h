@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LGCN_ABI_VERSION 1
+#define LGCN_ABI_VERSION 2
 
 #define LGCN_ERR_INVALID_ARG (-1)
 #define LGCN_ERR_UNSUPPORTED (-2)
@@ -41,6 +41,9 @@ extern "C" {
 #define LGCN_HUB_DEG 256
 #define LGCN_SEG_EDGES 1024
 #define LGCN_MAX_PEERS 8
+/* the sampler gives up on a negative after this many rejected candidates in a row (the sample is
+ * then dropped like an empty user) instead of spinning forever like negative_sample.py:121-126 */
+#define LGCN_MAX_NEG_TRIES 256
 
 typedef void* lgcn_stream_t; /* cudaStream_t */
 
@@ -137,6 +140,11 @@ typedef struct lgcn_layer_args {
    * probability keep_prob and rescaled by 1/keep_prob, independently per direction) passes
    * mask/keep_prob here; the backward pass passes the weights of the REVERSE entries. */
   const float* edge_w;
+  /* grad_mode 2 only: dst[i] (or the peers' rows, with n_dst_peers) receives src_scale[i] * E_new[i]
+   * — the pre-scaled layer-0 source of the NEXT step's forward pass — instead of the pre-scaled
+   * t_i.  The first layer of the next propagation then gathers it with scale_src = 0 (and, in the
+   * row-partitioned case, needs no separate exchange of the updated table). */
+  int push_emb;
 } lgcn_layer_args_t;
 
 int lgcn_propagate_layer(const lgcn_graph_t* g /*HOST*/, const lgcn_layer_args_t* a /*HOST*/,
@@ -169,12 +177,40 @@ int lgcn_exchange_rows_push(const float* tab_a, const float* tab_b, int d, const
  *   G[u_b] += s_b (out[n+neg_b] - out[n+pos_b]);  G[n+pos_b] -= s_b out[u_b];
  *   G[n+neg_b] += s_b out[u_b],  s_b = loss_scale * sigmoid(x_b) / B
  *   cnt[row]  += 1 for each of the 3 rows of every sample
- * G and cnt must be zero on entry.  work: float[2*B] + int32[1] (zeroed once).
+ * G and cnt must be zero on entry.  work: float[2*B]; work_counter: int32[2], zeroed once by the
+ * caller: [0] CTA arrival counter (self-resetting), [1] number of samples SKIPPED because an id
+ * was outside [0, n_users) / [0, n_nodes - n_users) — the reference's IndexError; sticky, the
+ * caller reads and clears it.  A step with a skipped sample reports NaN in loss_out[0..3].
  * ------------------------------------------------------------------------ */
 int lgcn_bpr_fwd_bwd(const float* out, const float* emb, const int64_t* users, const int64_t* pos,
                      const int64_t* neg, int64_t batch, int64_t n_users, int64_t n_nodes, int d,
                      float decay, float loss_scale, float* G, int32_t* cnt, float* loss_out,
                      float* work, int32_t* work_counter, lgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Row-partitioned BPR step (the reference's ddp_lgcn.py:476-515 trains replicas, the
+ * partition is _split_A_hat, dataloader.py:195-205, promoted to ranks).
+ *
+ * lgcn_padded_ids: global (user, pos, neg) ids -> padded row ids of the partition, ids[3B] =
+ *   [users | n+pos | n+neg]: padded = owner * rows_per_rank + side_off[side][owner] + (id - cuts[side][owner]).
+ *   cuts int64[2][world+1], side_off int64[2][world] (device).  Out-of-range ids are counted in
+ *   *status (the reference's IndexError) and mapped to a valid row.
+ * lgcn_bpr_fwd_bwd_rows: lgcn_bpr_fwd_bwd on the compact table rows[3B][2d] = [light_out | E] that
+ *   lgcn_exchange_rows_push filled (sample b = rows b, B+b, 2B+b).  Gradient rows are added to this
+ *   rank's G / cnt shard where padded / rows_per_rank == rank and, scaled by dinv_pad[padded], to
+ *   row `padded` of g0_full [world*rows_per_rank, d] fp32 (may be NULL) — the pre-scaled layer-0
+ *   source of the backward pass, built locally instead of exchanging the G shards.
+ * lgcn_zero_rows: table[ids[i]] = 0 (clears exactly the rows the step touched in g0_full).
+ * ------------------------------------------------------------------------ */
+int lgcn_padded_ids(const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t batch,
+                    int64_t n_users, int64_t n_nodes, const int64_t* cuts, const int64_t* side_off,
+                    int world, int64_t rows_per_rank, int64_t* padded_ids, int32_t* status,
+                    lgcn_stream_t stream);
+int lgcn_bpr_fwd_bwd_rows(const float* rows, const int64_t* padded_ids, int64_t batch, int d,
+                          int64_t rows_per_rank, int rank, float decay, float loss_scale, float* G,
+                          int32_t* cnt, float* g0_full, const float* dinv_pad, float* loss_out,
+                          float* work, int32_t* work_counter, lgcn_stream_t stream);
+int lgcn_zero_rows(float* table, int d, const int64_t* ids, int64_t n_ids, lgcn_stream_t stream);
 
 /* Adam bookkeeping: ++(*step) and adam_hp = {lr / (1-beta1^t), sqrt(1-beta2^t)}
  * in double precision like torch.optim.Adam's Python scalars. */
@@ -193,7 +229,8 @@ int lgcn_adam_step(float* param, const float* grad, float* m, float* v, int64_t 
  * Philox4x32-10(key=(seed_lo,seed_hi), ctr=(i_lo,i_hi,j/4,epoch)); draw 0 picks
  * the user (mulhi32(r,n_users)), draw 1 the positive from the FILE-ORDER list
  * (:119-120), draws 2.. the first item not contained in the user's positives
- * (:121-126, membership by binary search in the sorted copy).  Users with an
+ * (:121-126, membership by binary search in the sorted copy; after LGCN_MAX_NEG_TRIES
+ * rejections in a row the sample is dropped, valid[i]=0).  Users with an
  * empty list get valid[i]=0 (:116-117).  Samples [first, first+count) are drawn
  * (a shard is a counter offset).  n_neg > 1 draws n_neg negatives per (user, positive) from the
  * following Philox words and emits n_neg flat rows (u, pos, neg_t) per sample — the batch layout

@@ -215,7 +215,8 @@ def sparse_graph_full(graph):
 # --------------------------------------------------------------------------
 def uniform_sample_core(all_pos: Sequence[np.ndarray], sample_users: np.ndarray,
                         next_int: Callable[[int, int], int], n_neg: int = 1,
-                        pos_index: Callable[[int, int, int], int] = None) -> np.ndarray:
+                        pos_index: Callable[[int, int, int], int] = None,
+                        max_tries: int = 0) -> np.ndarray:
     """The reference's per-sample decision procedure, RNG factored out.
 
     negative_sample.py:113-130: for each drawn user IN ORDER: empty positive
@@ -224,6 +225,9 @@ def uniform_sample_core(all_pos: Sequence[np.ndarray], sample_users: np.ndarray,
     randint(m_items) whose value is not contained in allPos[user] (:121-126).
     `next_int(i, k)` returns the next draw in [0,k) for sample i.  `pos_index(i, user, len)`
     replaces the uniform positive pick (negative_sample.py:53-56, weighted by probs[user]).
+    `max_tries` > 0 (the GPU spec, LGCN_MAX_NEG_TRIES): after that many rejected candidates in a
+    row the sample and the rest of its negatives are dropped — the reference's `while True` never
+    returns for a user whose positives cover every item.
     """
     S = []
     for i, user in enumerate(sample_users):
@@ -232,10 +236,17 @@ def uniform_sample_core(all_pos: Sequence[np.ndarray], sample_users: np.ndarray,
             continue
         positem = P[next_int(i, len(P)) if pos_index is None else pos_index(i, int(user), len(P))]
         for _ in range(n_neg):  # n_neg > 1: flat (u, pos, neg_t) rows, the lgcnssm.py:141 batch layout
+            tries, neg = 0, None
             while True:
+                if max_tries and tries == max_tries:
+                    neg = None
+                    break
                 neg = next_int(i, -1)
+                tries += 1
                 if neg in P:
                     continue
+                break
+            if neg is None:
                 break
             S.append([int(user), int(positem), int(neg)])
     return np.array(S, dtype=np.int64).reshape(-1, 3)
@@ -255,6 +266,8 @@ def uniform_sample_mt(all_pos, n_users: int, m_items: int, count: int) -> np.nda
 
     return uniform_sample_core(all_pos, sample_users, next_int)
 
+
+MAX_NEG_TRIES = 256   # include/lgcn_b200.h LGCN_MAX_NEG_TRIES
 
 _PH_M0, _PH_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 _PH_W0, _PH_W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
@@ -334,7 +347,8 @@ def uniform_sample_philox(all_pos: Sequence[np.ndarray], n_users: int, m_items: 
         return min(j, n - 1)
 
     valid = np.array([len(all_pos[int(u)]) > 0 for u in sample_users], dtype=bool)
-    S = uniform_sample_core(all_pos, sample_users, next_int, n_neg, pos_index if pos_cdf is not None else None)
+    S = uniform_sample_core(all_pos, sample_users, next_int, n_neg, pos_index if pos_cdf is not None else None,
+                            max_tries=MAX_NEG_TRIES)
     return S, valid
 
 

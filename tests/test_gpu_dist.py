@@ -88,3 +88,61 @@ def test_row_partitioned_training_matches_reference_2gpu(exchange, partition):
             assert e_emb < 1e-6, e_emb
             assert same > 0.999, same
         assert ret[0][1] == ret[1][1]  # the loss is identical on every rank
+
+
+def _worker_partial(rank, world, port, ret, exchange):
+    """full, partial, full, full batches: the captured step graph must survive the eager partial batch
+    (grow-only scratch), and an eval propagation between steps (the pre-scaled table is re-pushed)."""
+    import torch.distributed as dist
+    from furusato_recommend_b200 import LightGCN
+    from furusato_recommend_b200.dataloader import BasicDataset
+    from furusato_recommend_b200.parallel import DistLightGCN
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        g = dict(np.load(GOLD))
+        d, K, B = (int(x) for x in g["config"])
+        lr, decay = (float(x) for x in g["hyper"])
+        cfg = dict(recdim=d, layer=K, lr=lr, decay=decay, bpr_batch_size=B, device=dev, test_u_batch_size=128,
+                   dist_exchange=exchange)
+        ds = BasicDataset(int(g["n_users"]), int(g["m_items"]), g["train_user"], g["train_item"], g["test_user"],
+                          g["test_item"], config=cfg, device=dev)
+        E0 = torch.from_numpy(g["E0"]).to(dev)
+        u, p, q = (torch.from_numpy(g[k]).to(dev) for k in ("batch_users", "batch_pos", "batch_neg"))
+        assert u.numel() == B
+        sm = LightGCN(cfg, ds)
+        with torch.no_grad():
+            sm.all_embedding.weight.copy_(E0)
+        sm.train()
+        dm = DistLightGCN(cfg, ds, rank, world)
+        dm.load_global_embedding(E0)
+        h = B // 3
+        losses, ref = [], []
+        for step, sl in enumerate((slice(0, B), slice(0, h), slice(0, B), slice(0, B))):
+            if step == 3:                      # an eval-only propagation between two replays
+                dm.computer_local()
+            losses.append(float(dm.fused_step(u[sl], p[sl], q[sl])))
+            ref.append(float(sm.stageOne(u[sl], p[sl], q[sl])))
+        dm.check_ids()
+        e_emb = float((dm.gather_embedding() - sm.all_embedding.weight.detach()).abs().max())
+        ret[rank] = (losses, ref, e_emb, dm._graph is not None)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("exchange", ["push", "nccl"])
+@pytest.mark.timeout(120)
+def test_partial_batch_between_graph_replays_2gpu(exchange):
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_partial, args=(world, port, ret, exchange), nprocs=world, join=True)
+        for rank in range(world):
+            losses, ref, e_emb, captured = ret[rank]
+            assert captured == (exchange == "push")
+            for a, b in zip(losses, ref):
+                assert abs(a - b) < 1e-5 * abs(b), (losses, ref)
+            assert e_emb < 1e-6, e_emb

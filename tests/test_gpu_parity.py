@@ -9,6 +9,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+from helpers import gap_rule  # noqa: E402
+
 from furusato_recommend_b200 import LightGCN, Trainer, UniformSample, ops  # noqa: E402
 from furusato_recommend_b200.dataloader import BasicDataset  # noqa: E402
 from furusato_recommend_b200.synthetic import bipartite  # noqa: E402
@@ -511,6 +513,15 @@ def test_eval_properties_cfg2_scale():
         s[srt[int(rp[u]):int(rp[u + 1])].long()] = -1024.0
         want = torch.sort(s, descending=True, stable=True)[1][:20]
         assert torch.equal(want, idx32[r].long())
+    # tensor-core lists vs the exact fp32 scores under the 2e-2 gap rule, on two row blocks
+    for lo in (0, len(users) - 1024):
+        blk = users[lo:lo + 1024]
+        dense_b = ops.score_dense_f32(*model.computer(), blk)
+        for r, u in enumerate(blk.tolist()):
+            dense_b[r, srt[int(rp[u]):int(rp[u + 1])].long()] = -1024.0
+        tol = 2e-2 * float(dense_b[dense_b > -1000].abs().max())
+        bad, compared, mism = gap_rule(idx16[lo:lo + 1024], dense_b, 20, tol)
+        assert bad == 0 and mism == 0, (bad, compared, mism)
     overlap = (idx16[:, :, None] == idx32[:, None, :]).any(-1).float().mean()
     assert float(overlap) > 0.97, float(overlap)
     res = Trainer(cfg, ds, model).test()
