@@ -3,19 +3,27 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-ours:       one "step" = one fused train step (K-layer propagation + BPR + backward
-            + Adam) on one batch of B=2048 triples of the cfg-2 graph
-            (BASELINE.json configs[1]); `value` = nnz(A_hat) * layers / t_step with
-            inputs resident in HBM, `e2e` = the same through LightGCN.stageOne()
-            with pinned HOST triples (H2D inside) and a D2H read of the loss.
-            The eval half of the metric (full-rank top-20 users/s) rides in "eval".
-reference:  the reference's CPU path (torch.sparse.mm xK + autograd + Adam, the
-            oracle port of model/lgcn.py:127-133) on this box's host cores.
+ours:       one "step" = one fused train step (K-layer propagation + BPR + backward + Adam) on one
+            batch of B = 2048 triples of the cfg-2 graph (BASELINE.json configs[1]; at N GPUs the
+            graph is N x cfg-2 and row-partitioned: weak scaling).  `value` = nnz(A_hat) * layers /
+            t_step with inputs resident in HBM, `e2e` = the same through the public API with pinned
+            HOST triples (H2D inside) and a D2H read of the loss.  The JSON line also carries
+              eval          full-rank top-20 users/s (tcgen05 scorer) + the cfg-5-shaped sweep
+              cfg3          BASELINE configs[2] (10 M x 2 M x 500 M edges, d = 128): the HBM-bound
+                            train step, strong scaling over the ranks, with the SpMM roofline
+              parity        the step being timed checked against the oracle (N = 1) or against the
+                            single-GPU model on the same graph (N > 1)
+              cpu_baseline  the reference's CPU path on this box's host cores (train step best-effort and
+                            as shipped, sampler, eval batch)
+              library_bar   stock torch on the same B200 (torch.sparse.mm + autograd + Adam; matmul + topk)
+reference:  the reference's CPU path (torch.sparse.mm x K + autograd + Adam, the oracle port of
+            model/lgcn.py:127-133) on this box's host cores, same config, same steps.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -32,6 +40,8 @@ METRIC = "LightGCN train edges*layers/sec (prop+BPR)"
 UNIT = "edges*layers/s"
 CFG2 = dict(n_users=30000, m_items=41000, n_interactions=1_250_000, seed=2020, d=64, layers=3, batch=2048,
             lr=1e-4, decay=1e-7)
+CFG3 = dict(CFG2, n_users=10_000_000, m_items=2_000_000, n_interactions=625_000_000, d=128)
+HBM = dict(CFG2, n_users=2_400_000, m_items=600_000, n_interactions=75_000_000, d=128)
 
 
 def parse():
@@ -44,14 +54,20 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg-3 (HBM-bound, strong-scaling) block")
+    ap.add_argument("--no-library-bar", action="store_true")
+    ap.add_argument("--no-bf16-block", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--cfg3-shape", default="cfg3", choices=["cfg3", "hbm"],
+                    help="graph of the cfg3 block: cfg3 = BASELINE configs[2]; hbm = 2.4M x 0.6M x 60M edges (quick)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "push", "nccl"],
                     help="N>1: push = all-gather fused into the SpMM epilogue over NVLink peer memory")
     ap.add_argument("--partition", default="auto", choices=["auto", "side_split", "two_sided"],
                     help="N>1: side_split = users on the first N/2 ranks, items on the rest (a row is only sent to "
                          "the other side); two_sided = every rank owns 1/N of both sides")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "hbm", "cfg3", "cfg4", "cfg5"],
-                    help="hbm: 2.4M x 0.6M x 60M-edge graph, d=128 (table >> L2) for the honest HBM roofline; "
-                         "cfg3: BASELINE configs[2], 10M x 2M x 500M edges, d=128 (graph built on device); "
+                    help="headline workload.  hbm: 2.4M x 0.6M x 60M-edge graph, d=128 (table >> L2); "
+                         "cfg3: BASELINE configs[2] as the headline; "
                          "cfg4: configs[3], LightGCNSSM 4-layer d=64, 256 negatives per positive on the same graph; "
                          "cfg5: configs[4], full-rank top-20 eval of --eval-users users x 2M items, user-sharded")
     ap.add_argument("--eval-users", type=int, default=1_000_000, help="cfg5: users scored (all ranks together)")
@@ -110,8 +126,9 @@ def measured_peaks():
     p = REPO / "MEASURED_PEAKS.json"
     if p.exists():
         j = json.loads(p.read_text())
-        return float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1424.4))), "measured"
-    return 6650.0, 1400.0, "fallback"  # B200_PROFILING.md fallback figures
+        return (float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1424.4))),
+                float(j.get("bf16_tflops", 1672.7)), "measured")
+    return 6650.0, 1400.0, 1650.0, "fallback"  # B200_PROFILING.md fallback figures
 
 
 def spmm_layer_bytes(nnz: int, N: int, d: int, s: int) -> int:
@@ -119,19 +136,35 @@ def spmm_layer_bytes(nnz: int, N: int, d: int, s: int) -> int:
     return nnz * (4 + d * s) + N * d * s + 2 * N * d * 4 + (N + 1) * 8
 
 
-# ------------------------------------------------------------------ reference arm / cpu baseline
-def cpu_train_steps(ds_arrays, steps: int, warmup: int, threads: int):
-    """The reference's CPU path (oracle port): unsplit torch.sparse.mm graph, autograd, torch Adam."""
+def workload_name(tag: str, world: int, K: int, d: int, B: int, n: int, m: int, nnz: int) -> str:
+    return (f"{tag}{' x%d' % world if world > 1 and tag == 'cfg-2' else ''}: LightGCN {K}-layer d={d} BPR B={B} on a synthetic "
+            f"five-core bipartite graph {n} users x {m} items, nnz(A_hat)={nnz}")
+
+
+def bench_config(tag: str, world: int, W: dict, n: int, m: int, nnz: int, B: int) -> dict:
+    """`config` of BOTH arms (the driver compares them): arm-neutral facts only."""
+    return {"workload": workload_name(tag, world, W["layers"], W["d"], B, n, m, nnz),
+            "graph": {"users": n, "items": m, "nnz": nnz}, "d": W["d"], "layers": W["layers"], "batch": B,
+            "lr": W["lr"], "decay": W["decay"],
+            "l2": "GPU arm: a 256 MiB buffer is written between timed steps (L2 flush, untimed); CPU arm: not applicable",
+            "parallelism": (f"{world} GPU(s); N > 1: the graph is N x cfg-2 (weak scaling), rows of A_hat and E "
+                            "partitioned by nnz over the ranks.  Reference arm: host cores of rank 0, same graph")}
+
+
+# ------------------------------------------------------------------ reference arm / cpu baselines
+def cpu_train_steps(ds_arrays, W: dict, steps: int, warmup: int, threads: int, folds: int = 0):
+    """The reference's CPU path (oracle port): torch.sparse.mm graph (split into `folds` row slices
+    when folds > 0, dataloader.py:195-205), autograd, torch Adam."""
     import numpy as np
     import torch
     from oracle import lgcn_oracle as orc
     torch.set_num_threads(threads)
     n, m, tu, ti = ds_arrays
     g = torch.Generator().manual_seed(2020)
-    E = torch.randn(n + m, CFG2["d"], generator=g) * 0.1
-    om = orc.OracleModel(n, m, tu, ti, E, CFG2["layers"], CFG2["lr"], CFG2["decay"])
+    E = torch.randn(n + m, W["d"], generator=g) * 0.1
+    om = orc.OracleModel(n, m, tu, ti, E, W["layers"], W["lr"], W["decay"], folds=folds)
     rng = np.random.default_rng(0)
-    B = CFG2["batch"]
+    B = W["batch"]
     times = []
     for s in range(warmup + steps):
         idx = rng.integers(0, len(tu), B)
@@ -141,109 +174,313 @@ def cpu_train_steps(ds_arrays, steps: int, warmup: int, threads: int):
         om.stage_one(users, pos, neg)
         if s >= warmup:
             times.append(time.perf_counter() - t0)
-    return sum(times) / len(times)
+    return sum(times) / len(times), om
 
 
-def workload_name(tag: str, world: int, K: int, d: int, B: int, n: int, m: int, nnz: int) -> str:
-    """config.workload of both arms (the driver compares them)."""
-    return (f"{tag}{' x%d' % world if world > 1 and tag == 'cfg-2' else ''}: LightGCN {K}-layer d={d} BPR B={B} on a synthetic "
-            f"five-core bipartite graph {n} users x {m} items, nnz(A_hat)={nnz}")
+def cpu_side_legs(ds, om, W: dict) -> dict:
+    """the reference's sampler (negative_sample.py:98-134, numpy MT19937 Python loop) and one
+    eval batch (trainer.py:130-138: re-propagation + matmul + exclude-list index_put + topk) on the host."""
+    import numpy as np
+    import torch
+    from oracle import lgcn_oracle as orc
+    out = {}
+    np.random.seed(2020)
+    cnt = 100_000
+    t0 = time.perf_counter()
+    S = orc.uniform_sample_mt(ds.allPos, ds.n_users, ds.m_items, cnt)
+    ts = time.perf_counter() - t0
+    out["sampler"] = {"value": len(S) / ts, "unit": "samples/s", "cores": 1, "kind": "port",
+                      "sample": f"{cnt} draws of UniformSample (numpy MT19937, Python loop)"}
+    users = torch.from_numpy(ds.test_users()[:10000].copy())
+    t0 = time.perf_counter()
+    rating = om.users_rating(users)                                 # re-propagates, like model/lgcn.py:121
+    orc.masked_topk(rating, [ds.allPos[int(u)] for u in users.tolist()], 20)
+    te = time.perf_counter() - t0
+    out["eval"] = {"value": len(users) / te, "unit": "users/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"one test_u_batch of {len(users)} users x {ds.m_items} items: propagation + matmul + "
+                             "exclude-list mask + top-20 (stable sort)"}
+    return out
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    import torch
     from furusato_recommend_b200.synthetic import bipartite
     world = max(1, int(args.gpus))   # the same graph our arm trains on at this N (cfg-2 x N, weak scaling)
-    n, m, tu, ti, su, si = bipartite(CFG2["n_users"] * world, CFG2["m_items"] * world, CFG2["n_interactions"] * world,
-                                     seed=CFG2["seed"])
+    W = CFG2
+    n, m, tu, ti, su, si = bipartite(W["n_users"] * world, W["m_items"] * world, W["n_interactions"] * world,
+                                     seed=W["seed"])
     nnz = 2 * int(tu.numel())
     threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 10))  # ~1 s per CPU step: keep the arm within a few minutes
-    warm = max(1, min(args.warmup, 2))
-    t = cpu_train_steps((n, m, tu.numpy(), ti.numpy()), steps, warm, threads)
-    val = nnz * CFG2["layers"] / t
-    sample = f"{steps} stageOne steps ({warm} warm-up) of the cfg-2 graph, unsplit torch.sparse.mm, B={CFG2['batch']}"
+    t, _ = cpu_train_steps((n, m, tu.numpy(), ti.numpy()), W, args.steps, args.warmup, threads)
+    val = nnz * W["layers"] / t
+    sample = (f"{args.steps} stageOne steps ({args.warmup} warm-up) of the cfg-2{' x%d' % world if world > 1 else ''} graph, "
+              f"unsplit torch.sparse.mm, B={W['batch']}, all {threads} host threads")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name("cfg-2", world, CFG2["layers"], CFG2["d"], CFG2["batch"], n, m, nnz),
-                   "path": "reference CPU path (oracle port, torch.sparse) on the host cores of rank 0"},
+        "config": bench_config("cfg-2", world, W, n, m, nnz, W["batch"]),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-# ------------------------------------------------------------------ our arm
-def run_ours(args, rank: int, world: int, local_rank: int):
+# ------------------------------------------------------------------ stock torch on the same GPU
+def library_bar(ds, W: dict, dev: str, steps: int, flush) -> dict:
+    """SURVEY §8d "library bar": what the reference itself runs on its default device (cuda,
+    world.py:48-49) — torch.sparse.mm over the coalesced COO graph x K (model/MF.py:196-205), autograd,
+    torch.optim.Adam (model/lgcn.py:63,127-133), and matmul + index_put_ + topk for one eval batch
+    (trainer.py:130-138, exclude lists prebuilt on the device: the host loop is not counted)."""
+    import torch
+    n, m, d, K, B = ds.n_users, ds.m_items, W["d"], W["layers"], W["batch"]
+    G = ds.getSparseGraph()                       # reference-format coalesced COO fp32 on the device
+    E = torch.nn.Parameter(torch.randn(n + m, d, device=dev) * 0.1)
+    opt = torch.optim.Adam([E], lr=W["lr"])
+    gen = torch.Generator(device=dev).manual_seed(1)
+    tu = torch.from_numpy(ds.trainUser).to(dev); ti = torch.from_numpy(ds.trainItem).to(dev)
+
+    def propagate(graph):
+        embs, cur = [E], E
+        for _ in range(K):
+            cur = torch.sparse.mm(graph, cur)
+            embs.append(cur)
+        out = torch.stack(embs, dim=1).mean(dim=1)
+        return out[:n], out[n:]
+
+    def step(graph):
+        idx = torch.randint(0, tu.numel(), (B,), device=dev, generator=gen)
+        users, pos = tu[idx], ti[idx]
+        neg = torch.randint(0, m, (B,), device=dev, generator=gen)
+        opt.zero_grad()
+        au, ai = propagate(graph)
+        ue, pe, ne = au[users], ai[pos], ai[neg]
+        u0, p0, n0 = E[users], E[n + pos], E[n + neg]
+        reg = 0.5 * (u0.norm(2).pow(2) + p0.norm(2).pow(2) + n0.norm(2).pow(2)) / float(B)
+        loss = torch.nn.functional.softplus((ue * ne).sum(1) - (ue * pe).sum(1)).mean() + W["decay"] * reg
+        loss.backward()
+        opt.step()
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for i in range(reps):
+            flush.fill_(i & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / reps / 1e3
+
+    nnz = int(G._nnz())
+    res = {"what": "stock torch %s on the same GPU: the reference's own ops on its default device" % torch.__version__}
+    t_coo = timed(lambda: step(G), steps)
+    res["train_coo"] = {"value": nnz * K / t_coo, "unit": UNIT, "ms_per_step": t_coo * 1e3,
+                        "ops": "torch.sparse.mm (coalesced COO, dataloader.py:207-213) x K + autograd + torch.optim.Adam"}
+    try:
+        Gc = G.to_sparse_csr()
+        t_csr = timed(lambda: step(Gc), steps)
+        res["train_csr"] = {"value": nnz * K / t_csr, "unit": UNIT, "ms_per_step": t_csr * 1e3,
+                            "ops": "the same with the graph converted to torch CSR"}
+    except Exception as e:  # noqa: BLE001 — a missing CSR autograd kernel must not kill the bench
+        res["train_csr"] = {"unavailable": repr(e)[:200]}
+    # eval batch
+    with torch.no_grad():
+        au, ai = propagate(G)
+        users = torch.from_numpy(ds.test_users()[:10000].copy()).to(dev)
+        rp, _, srt = ds.pos_csr()
+        lens = (rp[users + 1] - rp[users])
+        rows = torch.repeat_interleave(torch.arange(len(users), device=dev), lens)
+        rp_h = rp.cpu()
+        cols = torch.cat([srt[int(rp_h[u]):int(rp_h[u + 1])] for u in users.tolist()]).long()
+
+        def eval_batch():
+            rating = torch.matmul(au[users], ai.t())
+            rating[rows, cols] = -float(1 << 10)
+            torch.topk(rating, k=20)
+
+        t_ev = timed(eval_batch, 5)
+    res["eval"] = {"value": len(users) / t_ev, "unit": "users/s",
+                   "ops": f"matmul + index_put_ + torch.topk for one batch of {len(users)} users x {m} items "
+                          "(trainer.py:130-138; exclude lists prebuilt on the device, propagation excluded)"}
+    del G, E, opt
+    return res
+
+
+# ------------------------------------------------------------------ timing helpers
+def time_steps(step, n_steps: int, flush, barrier):
+    import torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+    barrier()
+    for i in range(n_steps):
+        flush.fill_(i & 0xFF)            # L2 flush between timed iterations (untimed)
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    barrier()
+    return sum(a.elapsed_time(b) for a, b in ev) / 1e3  # seconds for n_steps
+
+
+def time_spmm_launches(model, step, n_steps: int, flush):
+    """Average duration of one lgcn_propagate_layer launch, live, with CUDA events around every launch
+    (eager launches: the graph replay cannot be timed per kernel)."""
+    import torch
+    from furusato_recommend_b200 import ops
+    spmm_ms = []
+    orig = ops.propagate_layer
+
+    def timed_layer(*a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); orig(*a, **kw); e1.record()
+        spmm_ms.append((e0, e1))
+    ops.propagate_layer = timed_layer
+    had_graph = getattr(model, "use_cuda_graph", False)
+    if had_graph:
+        model.use_cuda_graph = False
+    try:
+        for i in range(n_steps):
+            flush.fill_(i & 0xFF)
+            step(i)
+        torch.cuda.synchronize()
+    finally:
+        ops.propagate_layer = orig
+        if had_graph:
+            model.use_cuda_graph = True
+    return sum(a.elapsed_time(b) for a, b in spmm_ms) / len(spmm_ms) / 1e3
+
+
+def roofline_block(nnz_loc: int, n_loc: int, d: int, s_bytes: int, spmm_avg_s: float, K: int, table_bytes: float,
+                   traffic_key: str) -> dict:
+    hbm_peak, _, _, which = measured_peaks()
+    layer_bytes = spmm_layer_bytes(nnz_loc, n_loc, d, s_bytes)
+    achieved = layer_bytes / spmm_avg_s / 1e9
+    compulsory = nnz_loc * 4 + (n_loc + 1) * 8 + 2 * n_loc * d * s_bytes
+    l2_resident = table_bytes < 100e6
+    gather_ceiling = 19800.0 if l2_resident else 7200.0
+    traffic, traffic_src = None, None
+    tp = REPO / "profiles" / "spmm_traffic.json"
+    if tp.exists():
+        tj = json.loads(tp.read_text())
+        traffic = tj.get(traffic_key)
+        traffic_src = tj.get("source", {}).get(traffic_key)
+    out = {"bound": "hbm", "kernel": "spmm_layer_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+           "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": which,
+           "bytes_per_launch": layer_bytes, "avg_launch_us": spmm_avg_s * 1e6, "launches_per_step": 2 * K,
+           # SURVEY 8d caveat: with an L2-resident table the gather term never reaches DRAM, so also report the
+           # compulsory DRAM bytes (col ids + rowptr + read/write of the [N, d] rows) and the measured ceiling of this
+           # access pattern (tools/gather_ceiling.cu: 19.8 TB/s from L2, 7.2 TB/s from HBM)
+           "compulsory_bytes_per_launch": compulsory, "compulsory_gbs": compulsory / spmm_avg_s / 1e9,
+           "gather_ceiling_gbs": gather_ceiling, "frac_of_gather_ceiling": achieved / gather_ceiling,
+           "note": ("SURVEY 8d gather model; the table is %.0f MB" % (table_bytes / 1e6)) +
+                   (" — L2-resident: the gathered rows never reach DRAM, `frac` is NOT an HBM fraction here (see "
+                    "dram_frac and the cfg3 block)" if l2_resident else " (>> 126 MB L2): HBM-bound")}
+    if traffic:
+        out["dram_gbs"] = traffic / spmm_avg_s / 1e9
+        out["dram_frac"] = traffic / spmm_avg_s / 1e9 / hbm_peak
+    return out
+
+
+# ------------------------------------------------------------------ parity inside the bench
+def parity_vs_oracle(model, ds, W: dict, batch) -> dict:
+    """N = 1: the model being timed against the oracle (CPU restatement of the reference) on the bench
+    graph: light_out, one train step's loss and the table after it."""
+    import torch
+    from oracle import lgcn_oracle as orc
+    E = model.all_embedding.weight.detach().cpu().clone()
+    om = orc.OracleModel(ds.n_users, ds.m_items, ds.trainUser, ds.trainItem, E, W["layers"], W["lr"], W["decay"])
+    # the model has taken steps already: give the oracle's Adam the same state
+    st = model.optim._init_state(model.all_embedding.weight)
+    om.optim.zero_grad()
+    om.optim.state[om.weight] = {"step": torch.tensor(float(st["step"].item())), "exp_avg": st["exp_avg"].detach().cpu().clone(),
+                                 "exp_avg_sq": st["exp_avg_sq"].detach().cpu().clone()}
+    model.eval()
+    u, i = model.computer()
+    with torch.no_grad():
+        ou, oi = om.computer()
+    ref = torch.cat([ou, oi])
+    e_out = float((torch.cat([u, i]).cpu() - ref).abs().max() / ref.abs().max())
+    model.train()
+    users, pos, neg = batch
+    loss = float(model.stageOne(users, pos, neg))
+    oloss = float(om.stage_one(users.cpu(), pos.cpu(), neg.cpu()))
+    e_emb = float((model.all_embedding.weight.detach().cpu() - om.weight.detach()).abs().max() / om.weight.detach().abs().max())
+    e_loss = abs(loss - oloss) / abs(oloss)
+    tol = 1e-5 if model.storage_dtype == torch.float32 else 2e-2
+    return {"against": "oracle (CPU restatement of model/MF.py:178-210 + model/lgcn.py:98-133) on the bench graph",
+            "light_out_rel_err": e_out, "loss_rel_err": e_loss, "emb_after_step_rel_err": e_emb, "tolerance": tol,
+            "ok": bool(e_out < tol and e_loss < tol and e_emb < tol)}
+
+
+def parity_vs_single_gpu(dm, ds, cfg: dict, rank: int, batch, tol: float) -> dict:
+    """N > 1: the row-partitioned model being timed against the single-GPU model on the SAME graph and
+    table (rank 0 builds it): unshard(light_out), the loss of two steps and the table after them."""
     import torch
     import torch.distributed as dist
-    from furusato_recommend_b200 import LightGCN, UniformSample, Trainer
-    from furusato_recommend_b200.dataloader import BasicDataset
-    from furusato_recommend_b200.synthetic import bipartite
-    from furusato_recommend_b200 import ops, metric as lmetric
+    from furusato_recommend_b200 import LightGCN
+    E0 = dm.gather_embedding()
+    dm.computer_local()
+    light = dm.gather_out()
+    users, pos, neg = batch
+    l1 = float(dm.fused_step(users, pos, neg))
+    l2 = float(dm.fused_step(users, pos, neg))
+    E2 = dm.gather_embedding()
+    res = torch.zeros(5, dtype=torch.float64, device=dm.device)
+    if rank == 0:
+        sm = LightGCN(dict(cfg, storage_dtype="fp32"), ds)
+        with torch.no_grad():
+            sm.all_embedding.weight.copy_(E0)
+        sm.eval()
+        su, si = sm.computer()
+        ref = torch.cat([su, si])
+        res[0] = float((light - ref).abs().max() / ref.abs().max())
+        sm.train()
+        s1 = float(sm.stageOne(users, pos, neg)); s2 = float(sm.stageOne(users, pos, neg))
+        res[1] = abs(l1 - s1) / abs(s1)
+        res[2] = abs(l2 - s2) / abs(s2)
+        W2 = sm.all_embedding.weight.detach()
+        res[3] = float((E2 - W2).abs().max() / W2.abs().max())
+        res[4] = 1.0
+        del sm
+    dist.broadcast(res, 0)
+    e = [float(x) for x in res[:4]]
+    return {"against": "single-GPU LightGCN (fp32) on the same graph, table and batches, built on rank 0",
+            "light_out_rel_err": e[0], "loss_rel_err": max(e[1], e[2]), "emb_after_2_steps_rel_err": e[3],
+            "tolerance": tol, "ok": bool(max(e) < tol)}
 
-    torch.cuda.set_device(local_rank)
-    dev = f"cuda:{local_rank}"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
 
-    # weak scaling: the graph grows with the number of GPUs (world x cfg-2), rows are
-    # partitioned over the ranks (nnz-balanced) and every layer all-gathers over NVLink
-    W = dict(CFG2)
-    if args.workload == "hbm":
-        W.update(n_users=2_400_000, m_items=600_000, n_interactions=75_000_000, d=128)
-    if args.workload == "cfg3":
-        W.update(n_users=10_000_000, m_items=2_000_000, n_interactions=625_000_000, d=128)
-    if args.workload == "cfg4":
-        W.update(n_users=10_000_000, m_items=2_000_000, n_interactions=625_000_000, d=64, layers=4, neg_size=256)
-    cfg = dict(recdim=W["d"], layer=W["layers"], lr=W["lr"], decay=W["decay"],
-               bpr_batch_size=W["batch"], device=dev, test_u_batch_size=10000, storage_dtype=args.storage,
-               dist_exchange=args.exchange, dist_partition=args.partition)
-    if args.workload in ("hbm", "cfg3", "cfg4"):
-        from furusato_recommend_b200.dataloader import DeviceDataset
-        n, m, tu, ti, su, si = bipartite(W["n_users"], W["m_items"], W["n_interactions"], seed=W["seed"], device=dev)
-        ds = DeviceDataset(n, m, tu, ti, su, si, config=cfg)
-        args.no_eval = True
-        args.no_cpu_baseline = True
-    else:
-        n, m, tu, ti, su, si = bipartite(W["n_users"] * world, W["m_items"] * world,
-                                         W["n_interactions"] * world, seed=W["seed"])
-        ds = BasicDataset(n, m, tu.numpy(), ti.numpy(), su.numpy(), si.numpy(), config=cfg, device=dev)
-    torch.manual_seed(2020 + rank)
-    K, d, B = W["layers"], W["d"], W["batch"]
-    J = int(W.get("neg_size", 1))
-    if J > 1:
-        if world != 1:
-            raise SystemExit("cfg4 is measured on one GPU")
-        from furusato_recommend_b200 import LightGCNSSM
-        cfg["neg_size"] = J
-        model = LightGCNSSM(cfg, ds)   # reference arithmetic: the BPR softplus over J*B flat triples per step
-        model.train()
-        nnz = model.graph.nnz
-        fused = model._fused_step
-        launches_per_step = 2 * K + 2
-        B = B * J                      # rows per step (model/lgcnssm.py:141)
-    elif world == 1:
+# ------------------------------------------------------------------ one train workload
+def build_model(W: dict, cfg: dict, ds, rank: int, world: int):
+    from furusato_recommend_b200 import LightGCN
+    K = W["layers"]
+    if world == 1:
         model = LightGCN(cfg, ds)
         model.train()
-        nnz = model.graph.nnz
-        fused = model._fused_step
-        launches_per_step = 2 * K + 2
-    else:
-        from furusato_recommend_b200.parallel import DistLightGCN
-        model = DistLightGCN(cfg, ds, rank, world)
-        nnz = ds.csr_graph().nnz
-        fused = model.fused_step
-        # SpMM x 2K, BPR, Adam tick; push exchange adds 2 scale_rows_push + 1 exchange_rows_push
-        launches_per_step = 2 * K + 2 + (3 if model.exchange == "push" else 0)
-    N = n + m
+        return model, model.graph.nnz, model._fused_step, 2 * K + 2
+    from furusato_recommend_b200.parallel import DistLightGCN
+    model = DistLightGCN(cfg, ds, rank, world)
+    # SpMM x 2K + id mapping + row exchange + BPR + Adam tick + row clear (push) | torch glue (nccl)
+    return model, ds.csr_graph().nnz, model.fused_step, 2 * K + (5 if model.exchange == "push" else 2)
 
-    S = UniformSample(ds, neg_ratio=J, seed=CFG2["seed"], epoch=0,
-                      count=min(ds.trainDataSize, (B // J) * (512 if J == 1 else 4)))
+
+def measure_train(args, W: dict, ds, cfg: dict, rank: int, world: int, dev: str, steps: int, warmup: int,
+                  n, m, parity_tol=None, clocks_idx=None):
+    """Times `steps` fused train steps of workload W on dataset ds; returns a dict of raw results."""
+    import torch
+    import torch.distributed as dist
+    from furusato_recommend_b200 import UniformSample
+    K, d, B = W["layers"], W["d"], W["batch"]
+    model, nnz, fused, launches_per_step = build_model(W, cfg, ds, rank, world)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    S = UniformSample(ds, seed=CFG2["seed"], epoch=0, count=min(ds.trainDataSize, B * 512))
+    t1.record()
+    torch.cuda.synchronize()
+    sampler = {"value": len(S) / (t0.elapsed_time(t1) / 1e3), "unit": "samples/s", "samples": int(len(S)),
+               "what": "UniformSample(dataset): Philox draw + rejection + order-preserving compaction, incl. the host "
+                       "sync that reads the row count"}
     n_batches = len(S) // B
     users, pos, neg = (S[:, j].contiguous() for j in range(3))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -257,45 +494,21 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    parity = None
+    if parity_tol is not None and world > 1:
+        parity = parity_vs_single_gpu(model, ds, cfg, rank, (users[:B], pos[:B], neg[:B]), parity_tol)
+    for i in range(warmup):
         step(i)
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)            # L2 flush between timed iterations (untimed)
-        ev[i][0].record()
-        step(args.warmup + i)
-        ev[i][1].record()
-    barrier()
-    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3  # seconds for K steps
-
-    # ---- per-launch SpMM time, live, with events around every propagate launch ----
-    spmm_ms = []
-    orig = ops.propagate_layer
-
-    def timed_layer(*a, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); orig(*a, **kw); e1.record()
-        spmm_ms.append((e0, e1))
-    import furusato_recommend_b200.model as _m
-    _m.ops.propagate_layer = timed_layer
-    had_graph = getattr(model, "use_cuda_graph", False)
-    if had_graph:
-        model.use_cuda_graph = False      # the per-launch events need the eager launches
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        step(i)
-    torch.cuda.synchronize()
-    _m.ops.propagate_layer = orig
-    if had_graph:
-        model.use_cuda_graph = True
-    spmm_avg_s = sum(a.elapsed_time(b) for a, b in spmm_ms) / len(spmm_ms) / 1e3
+    clocks = None
+    if clocks_idx is not None:
+        clocks = ClockSampler(clocks_idx)
+        clocks.start()
+    t_dev = time_steps(lambda i: step(warmup + i), steps, flush, barrier)
+    spmm_avg_s = time_spmm_launches(model, step, min(steps, 10), flush)
 
     # ---- e2e: public API with pinned host triples, H2D + loss D2H inside the timed region ----
-    S_host = S.cpu()
+    S_host = S[: n_batches * B].cpu()
     hu, hp, hn = (S_host[:, j].contiguous().pin_memory() for j in range(3))
 
     def e2e_step(b):
@@ -308,25 +521,186 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         e2e_step((i % n_batches) * B)
     e1.record()
     barrier()
     t_e2e = e0.elapsed_time(e1) / 1e3
-    # the timed regions are a few tens of ms; keep the same step running ~1.5 s more so the
-    # 100 ms nvidia-smi sampler sees the clocks / throttle reasons of THIS workload under load
-    t_end = time.perf_counter() + 1.5
-    i = 0
-    while time.perf_counter() < t_end:
-        step(i)
-        i += 1
-        if i % 64 == 0:
-            torch.cuda.synchronize()
+    clk = None
+    if clocks is not None:
+        # the timed regions are a few tens of ms; keep the same step running ~1.5 s more so the 100 ms
+        # nvidia-smi sampler sees the clocks / throttle reasons of THIS workload under load
+        t_end = time.perf_counter() + 1.5
+        i = 0
+        while time.perf_counter() < t_end:
+            step(i)
+            i += 1
+            if i % 64 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        clk = clocks.stop()
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e, spmm_avg_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, spmm_avg_s = (float(x) for x in t)
+    if parity_tol is not None and world == 1:
+        parity = parity_vs_oracle(model, ds, W, (users[:B], pos[:B], neg[:B]))
+    return dict(model=model, nnz=nnz, t_dev=t_dev, t_e2e=t_e2e, spmm_avg_s=spmm_avg_s, steps=steps,
+                launches_per_step=launches_per_step, clocks=clk, parity=parity, sampler=sampler, flush=flush,
+                batch=(users[:B], pos[:B], neg[:B]))
+
+
+def eigen_parity(model, ds, world: int, rank: int, dev: str) -> dict:
+    """Size-independent propagation check at the benchmarked size: A_hat (D^1/2 v) = D^1/2 v for any
+    column pattern v, so with E = sqrt(deg) (x) v the layer mean returns E itself (isolated nodes: 0)."""
+    import torch
+    g = ds.csr_graph()
+    deg = (g.rowptr[1:] - g.rowptr[:-1]).to(torch.float32)
+    d = model.latent_dim if world == 1 else model.d
+    v = torch.linspace(0.5, 1.5, d, device=dev)
+    if world == 1:
+        w = model.all_embedding.weight
+        keep = w.detach().clone()
+        with torch.no_grad():
+            w.copy_(deg.sqrt()[:, None] * v[None, :])
+        model.eval()
+        u, i = model.computer()
+        err = float((torch.cat([u, i]) - w.detach()).abs().max() / w.detach().abs().max())
+        with torch.no_grad():
+            w.copy_(keep)
+        model.train()
+        del keep
+    else:
+        import torch.distributed as dist
+        keep = model.emb.clone()
+        full = deg.sqrt()[:, None] * v[None, :]
+        model.load_global_embedding(full)
+        del full
+        out = model.computer_local()
+        e = (out - model.emb).abs().max() / model.emb.abs().max().clamp_min(1e-30)
+        e = e.to(torch.float64).reshape(1)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        err = float(e)
+        model.emb.copy_(keep)
+        model.prop.x0_valid = False if hasattr(model.prop, "x0_valid") else None
+        del keep
+    tol = 1e-5 if (model.storage_dtype if world == 1 else model.prop.storage_dtype) == torch.float32 else 2e-2
+    return {"property": "A_hat * (sqrt(deg) (x) v) = sqrt(deg) (x) v, so computer() must return the table itself",
+            "max_rel_err": err, "tolerance": tol, "ok": bool(err < tol)}
+
+
+def run_cfg3_block(args, rank: int, world: int, local_rank: int) -> dict:
+    """BASELINE configs[2]: 10 M users x 2 M items x 500 M train edges, d = 128, K = 3 — ONE graph, rows
+    partitioned over the ranks (strong scaling).  Its embedding table is 6.1 GB, so the SpMM is HBM-bound:
+    this block carries the honest roofline fraction north_star asks for."""
+    import torch
+    import torch.distributed as dist
+    from furusato_recommend_b200.dataloader import DeviceDataset
+    from furusato_recommend_b200.synthetic import bipartite
+    dev = f"cuda:{local_rank}"
+    W = dict(CFG3 if args.cfg3_shape == "cfg3" else HBM)
+    t_build = time.perf_counter()
+    n, m, tu, ti, su, si = bipartite(W["n_users"], W["m_items"], W["n_interactions"], seed=W["seed"], device=dev)
+    cfg = dict(recdim=W["d"], layer=W["layers"], lr=W["lr"], decay=W["decay"], bpr_batch_size=W["batch"], device=dev,
+               test_u_batch_size=10000, storage_dtype=args.storage, dist_exchange=args.exchange,
+               dist_partition=args.partition)
+    ds = DeviceDataset(n, m, tu, ti, su, si, config=cfg)
+    ds.csr_graph()
     torch.cuda.synchronize()
-    clk = clocks.stop()
+    t_build = time.perf_counter() - t_build
+    steps, warmup = max(3, min(args.steps, 10)), max(3, min(args.warmup, 3))
+    r = measure_train(args, W, ds, cfg, rank, world, dev, steps, warmup, n, m)
+    model = r["model"]
+    par = eigen_parity(model, ds, world, rank, dev)
+    K, d, B = W["layers"], W["d"], W["batch"]
+    nnz, N = r["nnz"], n + m
+    s_bytes = 2 if args.storage == "bf16" else 4
+    tag = "cfg-3" if args.cfg3_shape == "cfg3" else "hbm-bound"
+    out = {"workload": workload_name(tag, world, K, d, B, n, m, nnz), "scaling": "strong",
+           "value": nnz * K / (r["t_dev"] / steps), "unit": UNIT, "ms_per_step": r["t_dev"] / steps * 1e3,
+           "steps": steps, "warmup": warmup,
+           "e2e": {"value": nnz * K / (r["t_e2e"] / steps), "unit": UNIT, "ms_per_step": r["t_e2e"] / steps * 1e3,
+                   "h2d_bytes_per_step": 3 * B * 8, "d2h_bytes_per_step": 4},
+           "gpu_launches": r["launches_per_step"] * steps,
+           "roofline": roofline_block(nnz // world, N // world, d, s_bytes, r["spmm_avg_s"], K, N * d * s_bytes,
+                                      f"{'cfg3' if args.cfg3_shape == 'cfg3' else 'hbm'}_dram_bytes_per_launch_{args.storage}"),
+           "parity": par, "setup_s": t_build,
+           "l2": "table %.1f GB >> 126 MB L2; the 256 MiB flush is still written between timed steps" % (N * d * s_bytes / 1e9)}
+    if world > 1:
+        out["parallelism"] = (f"{world} GPUs, {'side_split' if getattr(model.part, 'side_split', False) else 'two_sided'} "
+                              f"partition, exchange={model.exchange}; roofline bytes are the rank-local share "
+                              "(peer stores of the fused all-gather not counted)")
+    del model, r, ds, tu, ti, su, si
+    gc.collect()
+    torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+    return out
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from furusato_recommend_b200 import Trainer
+    from furusato_recommend_b200.dataloader import BasicDataset
+    from furusato_recommend_b200.synthetic import bipartite
+    from furusato_recommend_b200 import ops, metric as lmetric
+
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    W = dict(CFG2)
+    if args.workload == "hbm":
+        W = dict(HBM)
+    if args.workload == "cfg3":
+        W = dict(CFG3)
+    if args.workload == "cfg4":
+        W = dict(CFG3, d=64, layers=4, neg_size=256)
+    cfg = dict(recdim=W["d"], layer=W["layers"], lr=W["lr"], decay=W["decay"],
+               bpr_batch_size=W["batch"], device=dev, test_u_batch_size=10000, storage_dtype=args.storage,
+               dist_exchange=args.exchange, dist_partition=args.partition)
+    big = args.workload in ("hbm", "cfg3", "cfg4")
+    if big:
+        from furusato_recommend_b200.dataloader import DeviceDataset
+        n, m, tu, ti, su, si = bipartite(W["n_users"], W["m_items"], W["n_interactions"], seed=W["seed"], device=dev)
+        ds = DeviceDataset(n, m, tu, ti, su, si, config=cfg)
+        args.no_eval = args.no_cpu_baseline = args.no_cfg3 = args.no_library_bar = args.no_bf16_block = True
+        args.no_parity = True
+    else:
+        # weak scaling: the graph grows with the number of GPUs (world x cfg-2), rows are
+        # partitioned over the ranks (nnz-balanced) and every layer exchanges over NVLink
+        n, m, tu, ti, su, si = bipartite(W["n_users"] * world, W["m_items"] * world,
+                                         W["n_interactions"] * world, seed=W["seed"])
+        ds = BasicDataset(n, m, tu.numpy(), ti.numpy(), su.numpy(), si.numpy(), config=cfg, device=dev)
+    torch.manual_seed(2020 + rank)
+    K, d, B = W["layers"], W["d"], W["batch"]
+    J = int(W.get("neg_size", 1))
+    N = n + m
+    tol = 1e-5 if args.storage == "fp32" else 2e-2
+
+    if J > 1:
+        r = measure_cfg4(args, W, ds, cfg, dev)
+        B = B * J
+    else:
+        r = measure_train(args, W, ds, cfg, rank, world, dev, args.steps, args.warmup, n, m,
+                          parity_tol=None if args.no_parity else tol, clocks_idx=local_rank)
+    model, nnz, t_dev, t_e2e, spmm_avg_s = r["model"], r["nnz"], r["t_dev"], r["t_e2e"], r["spmm_avg_s"]
+    flush = r["flush"]
+    launches_per_step, clk, sampler_info, parity_info = r["launches_per_step"], r["clocks"], r["sampler"], r["parity"]
+    exch = getattr(model, "exchange", None)
+    partn = None if world == 1 else ("side_split" if getattr(model.part, "side_split", False) else "two_sided")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     # ---- eval half of the metric: full-rank top-20 users/s ----
     eval_info = None
+    _, peak_tf, peak_tf_burst, _ = measured_peaks()
     if not args.no_eval and world == 1:
         model.eval()
         tr = Trainer(cfg, ds, model)
@@ -334,22 +708,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(); model.computer(); p1.record()
         rp, srt = ds.test_csr()
-        peak_tf = measured_peaks()[1]
 
         def eval_pass(precision):
             sums = torch.zeros((4, 2), dtype=torch.float64, device=dev)
             idx, _ = model.getUsersTopK(ev_users, 20, precision=precision)   # one launch: nothing is materialised
             lmetric.batch_metric_sums(idx, ev_users, rp, srt, (10, 20), sums)
             return sums
-
-        def timed(fn, reps):
-            fn(); torch.cuda.synchronize()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            for _ in range(reps):
-                fn()
-            a1.record(); torch.cuda.synchronize()
-            return a0.elapsed_time(a1) / 1e3 / reps
 
         t_tc = timed(lambda: eval_pass("bf16"), 5)
         t_f32 = timed(lambda: eval_pass("fp32"), 3)
@@ -361,41 +725,26 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         t_eval_e2e = time.perf_counter() - w0
         model.eval_precision = "fp32"
         res32 = tr.test()
+        model.eval_precision = "bf16"
         flops = 2.0 * len(ev_users) * m * d
         eval_info = {"metric": "full-rank top-20 eval users/sec (score+mask+top-k+metrics)",
                      "value": len(ev_users) / t_tc, "unit": "users/s", "users": int(len(ev_users)), "items": m,
                      "precision": "bf16 tcgen05 (fp32 accumulate)", "propagation_ms": p0.elapsed_time(p1),
                      "e2e": {"value": len(ev_users) / t_eval_e2e, "unit": "users/s"},
                      "tflops": flops / t_tc / 1e12, "tensor_peak_tflops": peak_tf,
+                     "note": "cfg-2 has 235 user tiles on 148 SMs and 311 item tiles: too small to fill the tensor pipe; "
+                             "the tensor-pipe figure is sweep_cfg5",
                      "fp32_exact_value": len(ev_users) / t_f32,
                      "recall@20": float(res["recall"][1]), "ndcg@20": float(res["ndcg"][1]),
                      "recall@20_fp32": float(res32["recall"][1]), "ndcg@20_fp32": float(res32["ndcg"][1])}
-        # cfg-5-shaped sweep: the tensor-pipe figure is only meaningful at m = 2M items
-        if not args.no_sweep:
-            U5, m5 = 148 * 128 * 4, 2_000_000
-            g5 = torch.Generator(device=dev).manual_seed(5)
-            ue5 = torch.randn(U5, d, generator=g5, device=dev) * 0.1
-            ie5 = torch.randn(m5, d, generator=g5, device=dev) * 0.1
-            ids5 = torch.arange(U5, device=dev)
-            npos = 50
-            rp5 = torch.arange(U5 + 1, device=dev, dtype=torch.int64) * npos
-            pos5 = torch.sort(torch.randint(0, m5, (U5, npos), generator=g5, device=dev, dtype=torch.int32), dim=1)[0]
-            pos5 = pos5.reshape(-1).contiguous()
-            t5 = timed(lambda: ops.score_topk(ue5, ie5, ids5, rp5, pos5, 20, precision="bf16"), 3)
-            fl5 = 2.0 * U5 * m5 * d
-            eval_info["sweep_cfg5"] = {"users": U5, "items": m5, "d": d, "k": 20, "masked_per_user": npos,
-                                       "value": U5 / t5, "unit": "users/s", "ms": t5 * 1e3,
-                                       "tflops": fl5 / t5 / 1e12, "frac_of_tensor_peak": fl5 / t5 / 1e12 / peak_tf,
-                                       "includes": "fp32->bf16 operand packing of both tables + score + mask + top-k"}
-            del ue5, ie5, pos5
         model.train()
+    # cfg-5-shaped sweep (every N: users are sharded, the item table is replicated, no collective)
+    if not args.no_eval and not args.no_sweep:
+        sw = sweep_cfg5(dev, d if d <= 64 else 64, rank, world, barrier)
+        if eval_info is None:
+            eval_info = {"metric": "full-rank top-20 eval users/sec, user-sharded"}
+        eval_info["sweep_cfg5"] = sw
 
-    # ---- max over ranks ----
-    if world > 1:
-        t = torch.tensor([t_dev, t_e2e, spmm_avg_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e, spmm_avg_s = (float(x) for x in t)
-    nnz_total = float(nnz)  # the partitioned graph is ONE graph: every rank reports its global nnz
     dist_eval = None
     if world > 1 and not args.no_eval:
         ev_users = torch.from_numpy(ds.test_users()).to(dev)
@@ -412,72 +761,191 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist_eval = {"metric": "full-rank top-20 eval users/sec, user-sharded (incl. all-gather of light_out)",
                      "value": len(ev_users) / float(te), "unit": "users/s", "users": int(len(ev_users)), "items": m,
                      "precision": "bf16 tcgen05 (fp32 accumulate)"}
+        if eval_info:
+            dist_eval["sweep_cfg5"] = eval_info.get("sweep_cfg5")
+
+    # ---- the same step with bf16 storage of the propagated activations (fp32 accumulate; 2e-2 tolerance) ----
+    bf16_block = None
+    if not args.no_bf16_block and args.storage == "fp32" and J == 1:
+        del model
+        r["model"] = None
+        gc.collect(); torch.cuda.empty_cache()
+        cfg_b = dict(cfg, storage_dtype="bf16")
+        rb = measure_train(args, W, ds, cfg_b, rank, world, dev, args.steps, args.warmup, n, m,
+                           parity_tol=None if args.no_parity else 2e-2)
+        bf16_block = {"what": "same workload, activations stored / exchanged as bf16 (fp32 accumulate, fp32 table, "
+                              "fp32 Adam); north_star tolerance 2e-2",
+                      "value": rb["nnz"] * K / (rb["t_dev"] / args.steps), "unit": UNIT,
+                      "ms_per_step": rb["t_dev"] / args.steps * 1e3,
+                      "e2e_ms_per_step": rb["t_e2e"] / args.steps * 1e3,
+                      "spmm_avg_launch_us": rb["spmm_avg_s"] * 1e6, "parity": rb["parity"], "exchange": exch}
+        del rb
+        gc.collect(); torch.cuda.empty_cache()
+        model = None
+
+    lib_bar = None
+    cpu_block = None
+    if rank == 0 and world == 1 and not args.no_library_bar:
+        lib_bar = library_bar(ds, W, dev, min(args.steps, 10), flush)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        arrays = (n, m, tu.cpu().numpy(), ti.cpu().numpy())
+        t_cpu, om = cpu_train_steps(arrays, W, 5, 2, threads)
+        cpu_block = {"value": nnz * K / t_cpu, "unit": UNIT, "cores": threads, "kind": "port",
+                     "sample": "5 stageOne steps (2 warm-up) of the same cfg-2 graph on the host: unsplit "
+                               "torch.sparse.mm x3 + autograd + torch Adam, B=2048 (best effort: all host threads)",
+                     "ms_per_step": t_cpu * 1e3}
+        legs = cpu_side_legs(ds, om, W)
+        del om
+        t_ship, _ = cpu_train_steps(arrays, W, 2, 1, 4, folds=1000)
+        cpu_block["as_shipped"] = {"value": nnz * K / t_ship, "unit": UNIT, "cores": 4, "kind": "port",
+                                   "ms_per_step": t_ship * 1e3,
+                                   "sample": "2 stageOne steps (1 warm-up) as the reference ships: OMP/MKL threads pinned "
+                                             "to 4 (world.py:3-4), A_split=True (world.py:46) with 1000 folds (parse.py:20)"}
+        cpu_block.update(legs)
+
+    # ---- cfg-3 block: the HBM-bound train step, strong scaling (frees the cfg-2 model first) ----
+    cfg3_block = None
+    if not args.no_cfg3:
+        model = None
+        r = None
+        gc.collect(); torch.cuda.empty_cache()
+        try:
+            cfg3_block = run_cfg3_block(args, rank, world, local_rank)
+        except Exception as e:  # noqa: BLE001 — report, do not lose the headline line
+            cfg3_block = {"error": repr(e)[:400]}
 
     if rank == 0:
-        hbm_peak, _, which = measured_peaks()
         s_bytes = 2 if args.storage == "bf16" else 4
-        layer_bytes = spmm_layer_bytes(nnz // world, N // world, d, s_bytes)  # per rank, per launch
-        achieved = layer_bytes / spmm_avg_s / 1e9
-        n_loc, nnz_loc = N // world, nnz // world
-        compulsory = nnz_loc * 4 + (n_loc + 1) * 8 + 2 * n_loc * d * s_bytes
-        gather_ceiling = 19800.0 if n_loc * d * s_bytes < 100e6 else 7200.0
-        traffic = None
-        tp = REPO / "profiles" / "spmm_traffic.json"
-        if tp.exists():
-            traffic = json.loads(tp.read_text()).get(f"{args.workload}_dram_bytes_per_launch_{args.storage}")
         ms = t_dev / args.steps * 1e3
+        tag = {'hbm': 'hbm-bound', 'cfg3': 'cfg-3', 'cfg2': 'cfg-2',
+               'cfg4': 'cfg-4 (lgcnssm, %d negatives per positive)' % J}[args.workload]
+        roof2 = roofline_block(nnz // world, N // world, d, s_bytes, spmm_avg_s, K, N * d * s_bytes / world,
+                               f"{args.workload}_dram_bytes_per_launch_{args.storage}")
         out = {
-            "metric": METRIC, "value": nnz_total * K / (t_dev / args.steps), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": float(nnz) * K / (t_dev / args.steps), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak" if args.workload == "cfg2" else "strong", "vs_baseline": None,
             "dtype": "f32" if args.storage == "fp32" else "bf16-storage/f32-acc",
             "data": "synthetic",
-            "config": {"workload": workload_name({'hbm': 'hbm-bound', 'cfg3': 'cfg-3', 'cfg2': 'cfg-2',
-                                                  'cfg4': 'cfg-4 (lgcnssm, %d negatives per positive)' % J}[args.workload],
-                                                 world, K, d, B, n, m, nnz),
-                       "l2": "256 MiB buffer written between timed steps (L2 flush, untimed)",
-                       "parallelism": "1 GPU" if world == 1 else
-                       f"{world} GPUs: rows partitioned by nnz; per-layer exchange = " +
-                       ("all-gather fused into the SpMM epilogue (NVLink peer stores, symmetric memory; "
-                        + ("bipartite side split: a row goes to the W/2 ranks of the other side only"
-                           if getattr(model.part, "side_split", False) else "every row to every rank")
-                        + ") (2K per step) + 3B-row exchange by owner peer stores; the whole step is one CUDA graph"
-                        if getattr(model, "exchange", "") == "push" else
-                        "ncclAllGather (2K per step) + one 3B-row all-reduce")},
-            "e2e": {"value": nnz_total * K / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 3 * B * 8,
+            "config": bench_config(tag, world, W, n, m, nnz, B),
+            "impl_notes": "1 GPU: 2K SpMM + BPR + Adam tick, one CUDA graph" if world == 1 else
+                          ("exchange=%s, partition=%s; per-layer all-gather fused into the SpMM epilogue (NVLink peer "
+                           "stores over symmetric memory), 2K-1 fused exchanges + one 3B-row owner-push per step, the "
+                           "whole step one CUDA graph" % (exch, partn)),
+            "e2e": {"value": float(nnz) * K / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": 3 * B * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps * 1e3},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "spmm_layer_kernel", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which,
-                         "bytes_per_launch": layer_bytes, "avg_launch_us": spmm_avg_s * 1e6,
-                         "launches_per_step": 2 * K,
-                         # SURVEY 8d caveat: with an L2-resident table the gather term never reaches DRAM, so also
-                         # report the compulsory DRAM bytes (col ids + rowptr + read/write of the [N, d] rows) and the
-                         # measured ceiling of this access pattern (tools/gather_ceiling.cu: 19.8 TB/s from L2,
-                         # 7.2 TB/s from HBM) the kernel is really up against
-                         "compulsory_bytes_per_launch": compulsory,
-                         "compulsory_gbs": compulsory / spmm_avg_s / 1e9,
-                         "gather_ceiling_gbs": gather_ceiling,
-                         "frac_of_gather_ceiling": achieved / gather_ceiling,
-                         "note": ("gather model; the table is %.0f MB" % (N * d * s_bytes / 1e6)) +
-                                 (" (L2-resident, so frac may exceed 1)" if N * d * s_bytes < 100e6 else " (>> 126 MB L2)")},
             "clocks": clk,
+            "sampler": sampler_info,
         }
-        if eval_info:
+        # the top-level roofline is the HBM-bound one when the cfg3 block ran; the cfg-2 figures (an
+        # L2-resident table) ride beside it
+        if cfg3_block and "roofline" in cfg3_block:
+            out["roofline"] = dict(cfg3_block["roofline"], workload=cfg3_block["workload"])
+            out["roofline_cfg2"] = roof2
+        else:
+            out["roofline"] = roof2
+        if parity_info is not None:
+            out["parity"] = parity_info
+        if eval_info and world == 1:
             out["eval"] = eval_info
         if dist_eval:
             out["eval"] = dist_eval
-        if not args.no_cpu_baseline and world == 1:
-            threads = os.cpu_count() or 1
-            t_cpu = cpu_train_steps((n, m, tu.cpu().numpy(), ti.cpu().numpy()), 5, 2, threads)
-            out["cpu_baseline"] = {"value": nnz * K / t_cpu, "unit": UNIT, "cores": threads, "kind": "port",
-                                   "sample": "5 stageOne steps (2 warm-up) of the same cfg-2 graph on the host: unsplit "
-                                             "torch.sparse.mm x3 + autograd + torch Adam, B=2048",
-                                   "ms_per_step": t_cpu * 1e3}
+        if bf16_block:
+            out["bf16_storage"] = bf16_block
+        if cfg3_block:
+            out["cfg3"] = cfg3_block
+        if lib_bar:
+            out["library_bar"] = lib_bar
+        if cpu_block:
+            out["cpu_baseline"] = cpu_block
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def timed(fn, reps):
+    import torch
+    fn(); torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(reps):
+        fn()
+    a1.record(); torch.cuda.synchronize()
+    return a0.elapsed_time(a1) / 1e3 / reps
+
+
+def sweep_cfg5(dev: str, d: int, rank: int, world: int, barrier) -> dict:
+    """cfg-5 shape (BASELINE configs[4]): 2 M items, d = 64, k = 20, 50 masked train positives per user;
+    every rank scores its own shard of 75 776 users (4 waves of 148 CTAs x 2 user tiles): users are
+    independent units, the item table is replicated, no collective."""
+    import torch
+    import torch.distributed as dist
+    from furusato_recommend_b200 import ops
+    _, peak_tf, peak_burst, _ = measured_peaks()
+    U5, m5, npos = 148 * 128 * 4, 2_000_000, 50
+    g5 = torch.Generator(device=dev).manual_seed(5 + rank)
+    gi = torch.Generator(device=dev).manual_seed(5)
+    ie5 = torch.randn(m5, d, generator=gi, device=dev) * 0.1
+    ue5 = torch.randn(U5, d, generator=g5, device=dev) * 0.1
+    ids5 = torch.arange(U5, device=dev)
+    rp5 = torch.arange(U5 + 1, device=dev, dtype=torch.int64) * npos
+    pos5 = torch.sort(torch.randint(0, m5, (U5, npos), generator=g5, device=dev, dtype=torch.int32), dim=1)[0]
+    pos5 = pos5.reshape(-1).contiguous()
+    ops.score_topk(ue5, ie5, ids5, rp5, pos5, 20, precision="bf16")
+    barrier()
+    t5 = timed(lambda: ops.score_topk(ue5, ie5, ids5, rp5, pos5, 20, precision="bf16"), 3)
+    if world > 1:
+        tt = torch.tensor([t5], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t5 = float(tt)
+    fl5 = 2.0 * U5 * m5 * d
+    del ue5, ie5, pos5
+    return {"users": U5 * world, "users_per_gpu": U5, "items": m5, "d": d, "k": 20, "masked_per_user": npos,
+            "value": U5 * world / t5, "unit": "users/s", "ms": t5 * 1e3, "n_gpus": world,
+            "tflops_per_gpu": fl5 / t5 / 1e12, "tflops": fl5 / t5 / 1e12,
+            "frac_of_tensor_peak": fl5 / t5 / 1e12 / peak_tf, "tensor_peak_tflops": peak_tf,
+            "frac_of_burst_peak": fl5 / t5 / 1e12 / peak_burst, "burst_peak_tflops": peak_burst,
+            "includes": "fp32->bf16 operand packing of both tables + score + mask + top-k; max over ranks"}
+
+
+def measure_cfg4(args, W: dict, ds, cfg: dict, dev: str):
+    """BASELINE configs[3]: LightGCNSSM, 256 negatives per positive (one GPU)."""
+    import torch
+    from furusato_recommend_b200 import LightGCNSSM, UniformSample
+    J, K, B = int(W["neg_size"]), W["layers"], W["batch"] * int(W["neg_size"])
+    cfg["neg_size"] = J
+    model = LightGCNSSM(cfg, ds)   # reference arithmetic: the BPR softplus over J*B flat triples per step
+    model.train()
+    S = UniformSample(ds, neg_ratio=J, seed=CFG2["seed"], epoch=0, count=(B // J) * 4)
+    n_batches = len(S) // B
+    users, pos, neg = (S[:, j].contiguous() for j in range(3))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(i):
+        b = (i % n_batches) * B
+        model._fused_step(users[b:b + B], pos[b:b + B], neg[b:b + B])
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(int(dev.split(":")[1])); clocks.start()
+    t_dev = time_steps(lambda i: step(args.warmup + i), args.steps, flush, torch.cuda.synchronize)
+    spmm = time_spmm_launches(model, step, min(args.steps, 5), flush)
+    S_host = S[: n_batches * B].cpu()
+    hu, hp, hn = (S_host[:, j].contiguous().pin_memory() for j in range(3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    model.stageOne(hu[:B], hp[:B], hn[:B]).item()
+    e0.record()
+    for i in range(args.steps):
+        b = (i % n_batches) * B
+        model.stageOne(hu[b:b + B], hp[b:b + B], hn[b:b + B]).item()
+    e1.record(); torch.cuda.synchronize()
+    return dict(model=model, nnz=model.graph.nnz, t_dev=t_dev, t_e2e=e0.elapsed_time(e1) / 1e3, spmm_avg_s=spmm,
+                steps=args.steps, launches_per_step=2 * K + 2, clocks=clocks.stop(), parity=None,
+                sampler={"value": None}, flush=flush, batch=None)
 
 
 # ------------------------------------------------------------------ cfg-5: eval sweep
@@ -551,7 +1019,7 @@ def run_cfg5(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t, t_e2e = float(tt[0]), float(tt[1])
     if rank == 0:
-        _, peak_tf, which = measured_peaks()
+        _, peak_tf, _, which = measured_peaks()
         flops = 2.0 * U * m5 * d
         n_launch = (U + chunk - 1) // chunk
         print(json.dumps({

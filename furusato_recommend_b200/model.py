@@ -36,6 +36,7 @@ class FusedAdam(torch.optim.Optimizer):
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.on_step = None   # callable: the kernels write the parameters through raw pointers
 
     def _init_state(self, p: torch.Tensor) -> dict:
         st = self.state[p]
@@ -57,6 +58,8 @@ class FusedAdam(torch.optim.Optimizer):
                 ops.adam_tick(st["step"], st["hp"], group["lr"], group["betas"])
                 ops.adam_step(p.data, p.grad.contiguous(), st["exp_avg"], st["exp_avg_sq"], st["hp"],
                               group["betas"], group["eps"])
+        if self.on_step is not None:
+            self.on_step()
         return loss
 
 
@@ -153,6 +156,13 @@ class LightGCN(nn.Module):
         self.use_cuda_graph = bool(config.get("cuda_graph", True))
         self._graph = None
         self._graph_key = None
+        # bf16 storage: the Adam epilogue of a fused step also emits ZE = bf16(dinv (.) E_new), the
+        # pre-scaled layer-0 source of the NEXT propagation (push_emb), so every forward layer gathers
+        # 2-byte elements.  fp32 storage keeps gathering E itself with dinv[j] applied on the fly
+        # (bit-stable against the round-1 goldens).  Symmetric normalisation only.
+        self.prescale_emb = bool(config.get("prescale_emb", self.storage_dtype == torch.bfloat16))
+        self._ze_key = None
+        self.optim.on_step = self._invalidate_derived
 
     def _build_graph(self, dataset: BasicDataset) -> CsrGraph:
         return dataset.csr_graph()
@@ -199,7 +209,7 @@ class LightGCN(nn.Module):
         t = self._bufs.get(name)
         if t is None:
             N, d, dev = self.num_users + self.num_items, self.latent_dim, self.all_embedding.weight.device
-            if name in ("Z0", "Z1"):
+            if name in ("Z0", "Z1", "ZE"):
                 t = torch.empty((N, d), dtype=self.storage_dtype, device=dev)
             elif name in ("ACC", "OUT"):
                 t = torch.empty((N, d), dtype=torch.float32, device=dev)
@@ -225,6 +235,25 @@ class LightGCN(nn.Module):
 
     def _zero_cnt(self) -> torch.Tensor:
         return self._buf("zero_cnt")
+
+    def _invalidate_derived(self) -> None:
+        """The table changed behind torch's version counter (raw-pointer kernels): drop what was
+        derived from it."""
+        self._eval_cache_valid = False
+        self._ze_key = None
+
+    def _ze(self, emb: torch.Tensor) -> Optional[torch.Tensor]:
+        """ZE = storage_dtype(dinv (.) E) for the CURRENT table, or None when the mode is off.  Normally
+        left behind by the previous fused step's Adam epilogue; rebuilt by one small kernel otherwise."""
+        w = self.all_embedding.weight
+        if not self.prescale_emb or self._col_scale is not None or emb.data_ptr() != w.data_ptr():
+            return None
+        ze = self._buf("ZE")
+        key = (w.data_ptr(), w._version)
+        if self._ze_key != key:
+            ops.scale_rows_push(w.detach(), self.graph.dinv, self.storage_dtype, [ze.data_ptr()], 0)
+            self._ze_key = key
+        return ze
 
     def _raise_on_bad_ids(self) -> None:
         """The BPR kernel skips (and counts) samples whose ids fall outside the table instead of
@@ -259,10 +288,11 @@ class LightGCN(nn.Module):
             self._sample_dropout()
         else:
             self._drop_fwd = self._drop_bwd = None
+        ze = self._ze(emb)
         for k in range(K):
             last = k == K - 1
             ops.propagate_layer(
-                g, emb if k == 0 else z[(k - 1) & 1], scale_src=(k == 0),
+                g, (emb if ze is None else ze) if k == 0 else z[(k - 1) & 1], scale_src=(k == 0 and ze is None),
                 dst=None if last else z[k & 1],
                 acc_in=emb if k == 0 else acc, acc_out=out if last else acc,
                 acc_scale=1.0 / (K + 1) if last else 1.0, edge_w=self._drop_fwd, **self._scales(False))
@@ -285,8 +315,10 @@ class LightGCN(nn.Module):
                 if adam is not None:
                     kw.update(adam_m=adam["exp_avg"], adam_v=adam["exp_avg_sq"], adam_hp=adam["hp"],
                               betas=adam["betas"], eps=adam["eps"], zero_base=K > 1)
-            ops.propagate_layer(g, G if j == 0 else z[(j - 1) & 1], scale_src=(j == 0),
-                                dst=None if last else z[j & 1], base=G, edge_w=edge_w, **kw,
+                    if self.prescale_emb and self._col_scale is None:
+                        kw.update(dst=self._buf("ZE"), push_emb=True)   # next step's layer-0 source
+            kw.setdefault("dst", None if last else z[j & 1])
+            ops.propagate_layer(g, G if j == 0 else z[(j - 1) & 1], scale_src=(j == 0), base=G, edge_w=edge_w, **kw,
                                 **self._scales(True))
 
     def computer(self) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -354,6 +386,7 @@ class LightGCN(nn.Module):
             self._capture_step_graph(B)
         for dst, src in zip(self._gbatch, (users, pos, neg)):
             dst.copy_(src, non_blocking=True)      # device slice or pinned host memory
+        self._ze(self.all_embedding.weight)        # the captured layer 0 reads ZE: make sure it is current
         self._graph.replay()
         self._eval_cache_valid = False
 
@@ -405,6 +438,8 @@ class LightGCN(nn.Module):
         if self.num_layers == 1:  # the single layer gathers from G, so it cannot clear it in flight
             G.zero_()
         self._eval_cache_valid = False
+        if self.prescale_emb and self._col_scale is None:
+            self._ze_key = (w.data_ptr(), w._version)   # ZE matches the updated table
 
     @torch.no_grad()
     def OneEpoch(self, user, pos, neg) -> torch.Tensor:
