@@ -77,6 +77,9 @@ SIGNATURES = {
     "lgcn_score_topk_workspace_bytes": (C.c_int64, [_I64, _I64, _I, _I]),
     "lgcn_score_topk_debug": (C.c_int, [_P, _P, _P, _I64, _I64, _I, _P, _P, _I, _F, _I, _P, _P, _P, _I64, _P, _P]),
     "lgcn_score_dense_f32": (C.c_int, [_P, _P, _P, _I64, _I64, _I, _P, _P]),
+    "lgcn_ingest_tiles": (C.c_int64, [_I64]),
+    "lgcn_ingest_count": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
+    "lgcn_ingest_emit": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _P, _P, _P, _I64, _P, _P]),
     "lgcn_rank_metrics": (C.c_int, [_P, _I64, _I, _P, _P, _P, C.POINTER(C.c_int32), _I, _P, _P, _P]),
 }
 

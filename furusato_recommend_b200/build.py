@@ -17,7 +17,7 @@ CSRC = PKG / "csrc"
 LIB = PKG / "liblgcn_b200.so"
 STAMP = PKG / ".liblgcn_b200.stamp"
 
-SOURCES = ["spmm.cu", "bpr.cu", "sampler.cu", "score_topk.cu", "score_topk_tc.cu", "metrics.cu"]
+SOURCES = ["spmm.cu", "bpr.cu", "sampler.cu", "score_topk.cu", "score_topk_tc.cu", "metrics.cu", "ingest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

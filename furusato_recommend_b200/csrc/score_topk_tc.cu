@@ -88,11 +88,34 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+// Cluster variants: one CTA fetches a 1/CL slice of the item tile and the copy engine delivers it to the
+// same shared-memory offset of every CTA of the cluster (each destination's mbarrier gets the bytes).
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+          "r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
+}
+// the same arrive delivered to the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -324,6 +347,7 @@ struct Params {
   int debug_mode;          // 0 = normal; pipeline experiments: 1 = epilogue skips the TMEM reads,
                            // 2 = TMEM reads only, 3 = reads + max tree, no candidate passes
   int acc16;               // 1: f16 accumulators, read back two per register (tcgen05.ld pack::16b)
+  int split;               // bulk copies per item tile (tuning: LGCN_TC_SPLIT)
 };
 
 // MT user tiles (128 rows each) share every item tile: the B operand stream is what bounds the MMA
@@ -337,7 +361,13 @@ struct Params {
 // the epilogue copies the whole 128-column accumulator of its user tile into registers and hands the
 // TMEM stage back BEFORE any selection work, so the MMA never waits for a warp that ran into
 // candidates; candidate values are then picked from registers with a warp-uniform switch.
-template <int D, int TN, int GROUPS, bool DUMP, bool ACC16, int MT, int NST, bool RS = false>
+// CL > 1 ("m2c2" / "m2c4"): CL CTAs form a thread-block cluster that SHARES the item-tile stream — every
+// CTA keeps its own users, accumulators and epilogue, but each item tile is fetched from L2 once per
+// cluster (CTA r loads slice r and multicasts it), and a ring stage is recycled when the MMAs of all CL
+// CTAs that read it have retired (multicast tcgen05.commit onto every CTA's `empty` barrier).  ncu of the
+// round-1 kernel shows the MMA issuer sleeping on the `full` barrier on every tile: the tile supply, not
+// the epilogue, bounds the pipeline (148 CTAs pulling the same 16 KB from L2 at the same time).
+template <int D, int TN, int GROUPS, bool DUMP, bool ACC16, int MT, int NST, bool RS = false, int CL = 1>
 __global__ void __launch_bounds__((kFrontWarps + 4 * GROUPS) * 32, 1)
 score_topk_tc_kernel(const Params p) {
   static_assert(!RS || (!ACC16 && GROUPS == MT && TN == 128), "register staging: fp32, one group per user tile, TN 128");
@@ -368,17 +398,19 @@ score_topk_tc_kernel(const Params p) {
   const uint32_t bar_afull = smem_u32(bars + 4 * kMaxStages);
   const int n_tiles = (p.m_items + TN - 1) / TN;
   const int S = p.stages;
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, CL);   // one commit per CTA that reads the stage
     }
     // one full/empty pair per (accumulator stage, user tile): the groups of a user tile hand their
     // accumulator back without waiting for the other user tile's warps
     for (int a = 0; a < NST * MT; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 128 * CG);
+      mbar_init(bar_tempty + 8 * a, 4 * CG);   // one elected lane per epilogue warp arrives
     }
     mbar_init(bar_afull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -390,6 +422,7 @@ score_topk_tc_kernel(const Params p) {
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // every CTA's barriers exist before a peer signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -402,10 +435,19 @@ score_topk_tc_kernel(const Params p) {
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % S;
         if (j >= S) mbar_wait(bar_empty + 8 * s, ((j / S) - 1) & 1);
-        mbar_expect_tx(bar_full + 8 * s, kBBytes);
-        bulk_g2s(smem_u32(sB + (size_t)s * kBBytes),
-                 reinterpret_cast<const unsigned char*>(p.b_packed) + (size_t)j * kBBytes, kBBytes,
-                 bar_full + 8 * s);
+        mbar_expect_tx(bar_full + 8 * s, kBBytes);   // the whole tile lands here, from CL senders
+        if constexpr (CL > 1) {
+          constexpr uint32_t kSlice = kBBytes / CL;
+          bulk_g2s_mc(smem_u32(sB + (size_t)s * kBBytes) + cta_rank * kSlice,
+                      reinterpret_cast<const unsigned char*>(p.b_packed) + (size_t)j * kBBytes + cta_rank * kSlice,
+                      kSlice, bar_full + 8 * s, kClusterMask);
+        } else {
+          const uint32_t piece = kBBytes / (uint32_t)p.split;
+          for (int c = 0; c < p.split; ++c)
+            bulk_g2s(smem_u32(sB + (size_t)s * kBBytes) + c * piece,
+                     reinterpret_cast<const unsigned char*>(p.b_packed) + (size_t)j * kBBytes + c * piece, piece,
+                     bar_full + 8 * s);
+        }
       }
       // tail: do not exit while a tcgen05.commit may still arrive on an smem barrier
       for (int j = n_tiles > S ? n_tiles - S : 0; j < n_tiles; ++j)
@@ -436,7 +478,8 @@ score_topk_tc_kernel(const Params p) {
           }
           tc_commit(bar_tfull + 8 * (a * MT + mt));   // this user tile's accumulator is ready for its groups
         }
-        tc_commit(bar_empty + 8 * s);   // smem stage reusable once these MMAs retire
+        // smem stage reusable once these MMAs retire — in every CTA that received the tile
+        if constexpr (CL > 1) tc_commit_mc(bar_empty + 8 * s, kClusterMask); else tc_commit(bar_empty + 8 * s);
       }
     }
   } else if (warp >= kFrontWarps) {
@@ -494,7 +537,8 @@ score_topk_tc_kernel(const Params p) {
         for (int q4 = 0; q4 < 4; ++q4) tc_ld32(tbase + (uint32_t)(32 * q4), r[q4]);
         tc_wait_ld();
         tc_fence_before();
-        mbar_arrive(bar_tempty + 8 * (a * MT + mt));   // the accumulator lives in registers now
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * (a * MT + mt));   // the accumulator lives in registers now
         const int item_tile0 = j * TN;
         if (DUMP) {
           if (live) {
@@ -671,8 +715,10 @@ score_topk_tc_kernel(const Params p) {
           if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
         }
       }
+      // one arrival per warp (128 same-address mbarrier arrives per hand-off serialise in shared memory)
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * (a * MT + mt));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * (a * MT + mt));
     }
 
     sel = sel_compact(sel, mv, mi, NT, p.k);
@@ -710,6 +756,7 @@ score_topk_tc_kernel(const Params p) {
   // ------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
@@ -721,7 +768,7 @@ constexpr size_t kSmemLimit = 227 * 1024;
 // Tuning overrides (A-B runs, pipeline experiments): read from the environment ONCE, at the first
 // launch of the process, never on the per-launch path.
 struct Tuning {
-  int debug_mode, trig;
+  int debug_mode, trig, split, stages;
   std::string layout;
 };
 static const Tuning& tuning() {
@@ -731,6 +778,11 @@ static const Tuning& tuning() {
     x.debug_mode = dbg ? atoi(dbg) : 0;
     const char* tg = getenv("LGCN_TC_TRIG");
     x.trig = tg ? atoi(tg) : 0;
+    const char* sp = getenv("LGCN_TC_SPLIT");
+    x.split = sp ? atoi(sp) : 1;
+    if (x.split != 1 && x.split != 2 && x.split != 4 && x.split != 8) x.split = 1;
+    const char* sg = getenv("LGCN_TC_STAGES");
+    x.stages = sg ? atoi(sg) : 0;
     const char* le = getenv("LGCN_TC_LAYOUT");
     x.layout = le ? le : "auto";
     return x;
@@ -738,7 +790,7 @@ static const Tuning& tuning() {
   return t;
 }
 
-template <int D, int TN, int GROUPS, int MT, int NST, bool RS = false>
+template <int D, int TN, int GROUPS, int MT, int NST, bool RS = false, int CL = 1>
 static int launch(const Params& p0, cudaStream_t st) {
   Params p = p0;
   constexpr int NT = GROUPS * 128;
@@ -751,15 +803,28 @@ static int launch(const Params& p0, cudaStream_t st) {
   }
   int stages = (int)((kSmemLimit - a_bytes - cand - tail) / b_bytes);
   if (stages > 8) stages = 8;   // kMaxStages barriers
+  if (tuning().stages > 1 && tuning().stages < stages) stages = tuning().stages;
   p.stages = stages;
   const size_t smem = a_bytes + (size_t)stages * b_bytes + cand + tail;
-  const int grid = (p.n_eval + kUM * MT - 1) / (kUM * MT);
+  const int grid = ((p.n_eval + kUM * MT * CL - 1) / (kUM * MT * CL)) * CL;   // whole clusters
   const int threads = (kFrontWarps + 4 * GROUPS) * 32;
 #define LGCN_TC_LAUNCH(DUMP_, ACC_)                                                                     \
   do {                                                                                                    \
-    auto kern = score_topk_tc_kernel<D, TN, GROUPS, DUMP_, ACC_, MT, NST, RS && !ACC_>;                   \
+    auto kern = score_topk_tc_kernel<D, TN, GROUPS, DUMP_, ACC_, MT, NST, RS && !ACC_, CL>;               \
     LGCN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    kern<<<grid, threads, smem, st>>>(p);                                                                 \
+    cudaLaunchConfig_t lc = {};                                                                           \
+    lc.gridDim = dim3((unsigned)grid);                                                                    \
+    lc.blockDim = dim3((unsigned)threads);                                                                \
+    lc.dynamicSmemBytes = smem;                                                                           \
+    lc.stream = st;                                                                                       \
+    cudaLaunchAttribute at[1];                                                                            \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                       \
+    at[0].val.clusterDim.x = CL;                                                                          \
+    at[0].val.clusterDim.y = 1;                                                                           \
+    at[0].val.clusterDim.z = 1;                                                                           \
+    lc.attrs = at;                                                                                        \
+    lc.numAttrs = CL > 1 ? 1 : 0;                                                                         \
+    LGCN_CUDA_OK(cudaLaunchKernelEx(&lc, kern, p));                                                       \
   } while (0)
   constexpr bool kAcc16Ok = (TN / 64) % (GROUPS / MT) == 0;   // a group needs whole 64-column chunks
   if (p.acc16) {
@@ -783,12 +848,12 @@ static size_t smem_need(int d, int tn, int groups, int mt, int cap) {
 }
 
 // One configuration: pack both operands for (TN, MT) and launch.
-template <int D, int TN, int GROUPS, int MT, int NST, bool RS = false>
+template <int D, int TN, int GROUPS, int MT, int NST, bool RS = false, int CL = 1>
 static int run_cfg(const float* user_emb, const float* item_emb, const int64_t* user_ids, int n_eval,
                    int m_items, const int64_t* pos_rowptr, const int32_t* pos_sorted, int k, int cap,
                    float mask_value, int32_t* out_idx, float* out_val, float* dense, void* workspace,
                    size_t workspace_bytes, int acc16, cudaStream_t st) {
-  const int64_t n_ut = ((n_eval + kUM * MT - 1) / (kUM * MT)) * MT, n_it = ((int64_t)m_items + TN - 1) / TN;
+  const int64_t n_ut = ((n_eval + kUM * MT * CL - 1) / (kUM * MT * CL)) * MT * CL, n_it = ((int64_t)m_items + TN - 1) / TN;
   const size_t a_total = (size_t)n_ut * kUM * D * 2, b_total = (size_t)n_it * TN * D * 2;
   if (workspace == nullptr || workspace_bytes < a_total + b_total) {
     set_last_error("score_topk (bf16) needs a %zu-byte workspace, got %zu", a_total + b_total,
@@ -828,7 +893,8 @@ static int run_cfg(const float* user_emb, const float* item_emb, const int64_t* 
   p.acc16 = acc16;
   p.debug_mode = tuning().debug_mode;
   p.trig = tuning().trig;
-  return launch<D, TN, GROUPS, MT, NST, RS>(p, st);
+  p.split = tuning().split;
+  return launch<D, TN, GROUPS, MT, NST, RS, CL>(p, st);
 }
 
 #define LGCN_TC_ARGS user_emb, item_emb, user_ids, n_eval, m_items, pos_rowptr, pos_sorted, k
@@ -855,6 +921,8 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
 #if LGCN_TC_RS
       if (layout == "m2rs") return run_cfg<D, 128, 2, 2, 2, true>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
 #endif
+      if (layout == "m2c2") return run_cfg<D, 128, 2, 2, 2, false, 2>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
+      if (layout == "m2c4") return run_cfg<D, 128, 2, 2, 2, false, 4>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
       if (layout == "m2g2" || layout == "auto") return run_cfg<D, 128, 2, 2, 2>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
     }
     if (k <= 20 && !acc16 && layout == "m2g4") return run_cfg<D, 128, 4, 2, 2>(LGCN_TC_ARGS, 32, LGCN_TC_TAIL);
@@ -879,9 +947,9 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
 }  // namespace tc
 
 size_t score_topk_tc_workspace(int64_t n_eval, int64_t m_items, int d) {
-  // covers every layout: user tiles rounded up to a pair (MT = 2), item tiles at the widest TN
+  // covers every layout: user tiles rounded up to whole clusters (MT = 2 x CL = 4), item tiles at the widest TN
   const int tn = d >= 128 ? 128 : 256;
-  const int64_t n_ut = ((n_eval + 2 * tc::kUM - 1) / (2 * tc::kUM)) * 2, n_it = (m_items + tn - 1) / tn;
+  const int64_t n_ut = ((n_eval + 8 * tc::kUM - 1) / (8 * tc::kUM)) * 8, n_it = (m_items + tn - 1) / tn;
   return (size_t)n_ut * tc::kUM * d * 2 + (size_t)n_it * tn * d * 2;
 }
 

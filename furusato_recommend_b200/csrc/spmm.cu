@@ -393,9 +393,12 @@ spmm_layer_kernel(const GraphDev g, const EpiDev p) {
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x < D) {
-      colsum = 0.f;
+      // up to ~1000 segment partials of a hub row: accumulated in fp64 (a sequential fp32 sum of n
+      // equal-sized terms drifts by ~n * 2^-24; 3e-5 on the largest cfg-3 hubs), still in segment order
+      double cs = 0.0;
       for (int q = 0; q < nseg; ++q)
-        colsum += __ldcg(g.partial + (int64_t)(seg0 + q) * D + threadIdx.x);
+        cs += (double)__ldcg(g.partial + (int64_t)(seg0 + q) * D + threadIdx.x);
+      colsum = (float)cs;
     }
   }
   __syncthreads();  // everyone is done reading red[*] before it is overwritten

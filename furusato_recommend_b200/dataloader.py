@@ -209,19 +209,37 @@ class Loader(BasicDataset):
     `for_lgbm` / `cold_start` splits (:100-113) are reference product features
     outside the hot path and are rejected explicitly."""
 
-    def __init__(self, config: dict, path: str = "./data/cf", device: Optional[str] = None):
+    def __init__(self, config: dict, path: str = "./data/cf", device: Optional[str] = None, ingest: str = "auto"):
         if config.get("for_lgbm") or config.get("cold_start"):
             raise NotImplementedError("for_lgbm / cold_start splits are outside the LightGCN hot path")
         suffix = config.get("suffix", "")
         self.path = path
-        tr_u, tr_i = self._parse(f"{path}/{suffix}/train{suffix}.txt", bool(config.get("test")))
-        te_u, te_i = self._parse(f"{path}/{suffix}/test{suffix}.txt", bool(config.get("test")))
+        dev = torch.device(device or config.get("device", "cuda:0"))
+        # "device": the file's bytes are parsed by the lgcn_ingest_* kernels; "host": the Python loop
+        # (the only one that honours --test's early stop, dataloader.py:122-124); "auto": device when
+        # the dataset lives on a GPU and --test is off
+        if ingest == "auto":
+            ingest = "device" if dev.type == "cuda" and torch.cuda.is_available() and not config.get("test") else "host"
+        parse = (lambda f: self._parse_device(f, dev)) if ingest == "device" else (lambda f: self._parse(f, bool(config.get("test"))))
+        self.ingest = ingest
+        tr_u, tr_i = parse(f"{path}/{suffix}/train{suffix}.txt")
+        te_u, te_i = parse(f"{path}/{suffix}/test{suffix}.txt")
         n = int(max(tr_u.max(initial=-1), te_u.max(initial=-1))) + 1
         m = int(max(tr_i.max(initial=-1), te_i.max(initial=-1))) + 1
         uniq = np.unique(tr_u)
         if len(uniq) and (np.any(np.diff(tr_u) < 0) or uniq[0] != 0 or uniq[-1] != len(uniq) - 1):
             raise ValueError("train file must list uids 0..n-1 in ascending order without gaps")
         super().__init__(n, m, tr_u, tr_i, te_u, te_i, config=config, device=device)
+
+    @staticmethod
+    def _parse_device(fname: str, device):
+        """The same (users, items) arrays from the GPU text parser (csrc/ingest.cu)."""
+        from . import ops
+        raw = np.fromfile(fname, dtype=np.uint8)
+        if raw.size == 0:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        u, i = ops.ingest_text(torch.from_numpy(raw).to(device))
+        return u.cpu().numpy(), i.cpu().numpy()
 
     @staticmethod
     def _parse(fname: str, truncate: bool):

@@ -342,3 +342,35 @@ def rank_metrics(topk: torch.Tensor, user_ids: torch.Tensor, test_rowptr: torch.
     else:
         sums += tmp
     return (sums, hits) if want_hits else sums
+
+
+def ingest_text(text: torch.Tensor):
+    """lgcn_ingest_*: raw bytes of a `uid item item ...\\n` file (uint8 CUDA tensor) -> (user int64[n],
+    item int64[n]) in file order, duplicates kept (reference dataloader.py:93-124).  Two host syncs:
+    the interaction count (to size the outputs) and the error flag."""
+    lib = _lib.load()
+    n_bytes = text.numel()
+    dev = text.device
+    n_tiles = int(lib.lgcn_ingest_tiles(n_bytes))
+    tile_tok = torch.zeros(max(n_tiles, 1), dtype=torch.int64, device=dev)
+    tile_uid = torch.zeros(max(n_tiles, 1), dtype=torch.int64, device=dev)
+    totals = torch.zeros(2, dtype=torch.int64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    with _on(text, tile_tok, tile_uid, totals, err) as st:
+        _lib.check(lib.lgcn_ingest_count(_chk(text, torch.uint8, "text"), n_bytes, tile_tok.data_ptr(), tile_uid.data_ptr(),
+                                         totals.data_ptr(), err.data_ptr(), st), "lgcn_ingest_count")
+        n_tok, n_uid = (int(x) for x in totals.tolist())
+        n = n_tok - n_uid
+        line_uid = torch.empty(max(n_uid, 1), dtype=torch.int64, device=dev)
+        user = torch.empty(n, dtype=torch.int64, device=dev)
+        item = torch.empty(n, dtype=torch.int64, device=dev)
+        line_of = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        _lib.check(lib.lgcn_ingest_emit(text.data_ptr(), n_bytes, tile_tok.data_ptr(), tile_uid.data_ptr(),
+                                        line_uid.data_ptr(), n_uid, user.data_ptr(), item.data_ptr(), line_of.data_ptr(),
+                                        n, err.data_ptr(), st), "lgcn_ingest_emit")
+    flag = int(err.item())
+    if flag & 1:
+        raise ValueError("interaction file holds a byte that is not a digit or whitespace (the reference's int() raises)")
+    if flag & 6:
+        raise ValueError(f"malformed interaction file (ingest error flag {flag})")
+    return user, item

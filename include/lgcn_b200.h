@@ -303,6 +303,28 @@ int lgcn_rank_metrics(const int32_t* topk, int64_t n_eval, int k, const int64_t*
                       const int32_t* ks /*HOST, ascending*/, int n_ks, double* sums, uint8_t* hits /* [n_eval,k] or NULL */,
                       lgcn_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Device-side ingest of the reference's interaction files.  Replaces the host
+ * Python loop of Loader.__init__ (dataloader.py:93-124 train, :126-150 test): each line is
+ * "uid item item ...\n"; every (uid, item) pair is appended to trainUser / trainItem in file
+ * order, duplicates kept.  `text` is the raw file in device memory (16-byte aligned).
+ *   lgcn_ingest_tiles(n_bytes)  -> number of 4 KiB tiles (sizes tile_tok / tile_uid)
+ *   lgcn_ingest_count           -> exclusive scans of the per-tile token / uid-token counts and
+ *                                  totals[0] = tokens, totals[1] = uid tokens (= non-empty lines);
+ *                                  interactions = totals[0] - totals[1]
+ *   lgcn_ingest_emit            -> user[i], item[i] (int64, file order), line_uid[l] = uid of the
+ *                                  l-th non-empty line, line_of[i] = line ordinal of interaction i
+ * err (device int32, zero on entry): bit 0 = a byte that is neither digit, space, tab, CR nor
+ * newline (the reference's int() raises ValueError), bit 1 = a token longer than 18 digits,
+ * bit 2 = counts and capacities disagree.
+ * ------------------------------------------------------------------------ */
+int64_t lgcn_ingest_tiles(int64_t n_bytes);
+int lgcn_ingest_count(const uint8_t* text, int64_t n_bytes, int64_t* tile_tok, int64_t* tile_uid,
+                      int64_t* totals, int32_t* err, lgcn_stream_t stream);
+int lgcn_ingest_emit(const uint8_t* text, int64_t n_bytes, const int64_t* tile_tok, const int64_t* tile_uid,
+                     int64_t* line_uid, int64_t n_lines_cap, int64_t* user, int64_t* item, int64_t* line_of,
+                     int64_t cap_items, int32_t* err, lgcn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

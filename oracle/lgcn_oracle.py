@@ -71,6 +71,29 @@ def norm_adj_coo(n_users: int, m_items: int, train_user, train_item):
     return row, col, val
 
 
+def norm_adj_scipy_as_shipped(n_users: int, m_items: int, train_user, train_item):
+    """The SAME matrix through the scipy route the reference takes as shipped (dataloader.py:226-244:
+    an empty dok -> lil, block assignment of R and R^T, back to dok, row sums, D^-1/2 as sp.diags, two
+    sparse products, csr).  Only used to TIME the reference's graph build (bench.py's `ingest` leg) and
+    to check that `norm_adj_coo` above yields the identical values; R = csr_matrix(ones, (u, i)) is the
+    commented-out `UserItemNet` of dataloader.py:164-165.  Returns scipy csr fp32."""
+    import scipy.sparse as sp
+    tu = np.asarray(train_user, dtype=np.int64)
+    ti = np.asarray(train_item, dtype=np.int64)
+    N = n_users + m_items
+    R = sp.csr_matrix((np.ones(len(tu)), (tu, ti)), shape=(n_users, m_items)).tolil()
+    adj = sp.dok_matrix((N, N), dtype=np.float32).tolil()
+    adj[:n_users, n_users:] = R
+    adj[n_users:, :n_users] = R.T
+    adj = adj.todok()
+    rowsum = np.array(adj.sum(axis=1))
+    with np.errstate(divide="ignore"):
+        d_inv = np.power(rowsum, -0.5).flatten()
+    d_inv[np.isinf(d_inv)] = 0.0
+    d_mat = sp.diags(d_inv)
+    return d_mat.dot(adj).dot(d_mat).tocsr()
+
+
 def sparse_graph(n_users: int, m_items: int, train_user, train_item, folds: int = 0):
     """torch sparse graph as `Loader.getSparseGraph` returns it.
 

@@ -368,7 +368,7 @@ def test_score_topk_bit_exact_on_own_scores(shape):
 
 def test_eval_matches_reference_topk_and_metrics(golden, tiny_lists):
     train, test = tiny_lists
-    model = golden_model(golden, weights="E2")
+    model = golden_model(golden, weights="E2", eval_precision="fp32")   # the exactness mode; default is bf16 (below)
     model.eval()
     users = torch.from_numpy(golden["eval_users"]).to(DEV)
     rating = model.getUsersRating(users)
@@ -389,6 +389,12 @@ def test_eval_matches_reference_topk_and_metrics(golden, tiny_lists):
     res = Trainer(model.config, model.dataset, model, topks=[int(k) for k in golden["topks"]]).test()
     for name in ("recall", "precision", "ndcg", "hr"):
         assert np.allclose(res[name], golden[f"metric_raw_{name}"], rtol=0, atol=2e-3), name
+    # the default evaluation path scores on the tcgen05 tensor cores (bf16 operands, fp32 accumulate)
+    dflt = golden_model(golden, weights="E2")
+    assert dflt.eval_precision == "bf16"
+    res16 = Trainer(dflt.config, dflt.dataset, dflt, topks=[int(k) for k in golden["topks"]]).test()
+    for name in ("recall", "precision", "ndcg", "hr"):
+        assert np.allclose(res16[name], golden[f"metric_raw_{name}"], rtol=0, atol=5e-3), name
 
 
 def test_rank_metrics_match_oracle(golden, tiny_lists):
@@ -407,7 +413,7 @@ def test_rank_metrics_match_oracle(golden, tiny_lists):
 
 
 def test_get_topk_list_format(golden):
-    model = golden_model(golden, weights="E2")
+    model = golden_model(golden, weights="E2", eval_precision="fp32")
     lists = Trainer(model.config, model.dataset, model).get_topk_list(k=50)  # eval.py:35-40 candidates
     assert sum(len(x) for x in lists) == len(golden["eval_users"])
     assert lists[0].dtype == torch.int64 and lists[0].shape[1] == 50 and not lists[0].is_cuda

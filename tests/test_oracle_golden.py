@@ -130,3 +130,13 @@ def test_philox_sampler_multi_negative_layout(tiny_lists, golden):
     assert S4.shape == (200, 3) and np.array_equal(S4[::4], S1)
     for u, p, q in S4:
         assert p in train[u] and q not in train[u]
+
+
+def test_scipy_as_shipped_build_equals_the_golden_graph(golden):
+    """The dok/lil route the reference ships (dataloader.py:226-244), which bench.py times, yields the
+    live reference's graph bit for bit — so timing it is timing the reference's own build."""
+    n, m = int(golden["n_users"]), int(golden["m_items"])
+    A = orc.norm_adj_scipy_as_shipped(n, m, golden["train_user"], golden["train_item"]).tocoo()
+    order = np.lexsort((A.col, A.row))
+    assert np.array_equal(A.row[order], golden["adj_row"]) and np.array_equal(A.col[order], golden["adj_col"])
+    assert np.array_equal(A.data[order].astype(np.float32), golden["adj_val"])
