@@ -67,6 +67,7 @@ SIGNATURES = {
     "lgcn_padded_ids": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _I, _I64, _P, _P, _P]),
     "lgcn_bpr_fwd_bwd_rows": (C.c_int, [_P, _P, _I64, _I, _I64, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "lgcn_zero_rows": (C.c_int, [_P, _I, _P, _I64, _P]),
+    "lgcn_ssm_fwd_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I, _I64, _I64, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     "lgcn_adam_tick": (C.c_int, [_P, _P, _D, _D, _D, _P]),
     "lgcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, _D, _D, _D, _P]),
     "lgcn_uniform_sample": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _I, C.c_uint64, C.c_uint32, _P, _P, _P]),

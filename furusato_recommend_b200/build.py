@@ -17,7 +17,7 @@ CSRC = PKG / "csrc"
 LIB = PKG / "liblgcn_b200.so"
 STAMP = PKG / ".liblgcn_b200.stamp"
 
-SOURCES = ["spmm.cu", "bpr.cu", "sampler.cu", "score_topk.cu", "score_topk_tc.cu", "metrics.cu", "ingest.cu"]
+SOURCES = ["spmm.cu", "bpr.cu", "sampler.cu", "score_topk.cu", "score_topk_tc.cu", "metrics.cu", "ingest.cu", "ssm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -33,7 +33,7 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "lgcn_b200.h"]):
+    for f in sorted([CSRC / x for x in SOURCES] + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "lgcn_b200.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())

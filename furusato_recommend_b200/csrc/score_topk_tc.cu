@@ -104,6 +104,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -404,7 +413,7 @@ score_topk_tc_kernel(const Params p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, CL);   // one commit per CTA that reads the stage
+      mbar_init(bar_empty + 8 * s, CL * MT);   // one commit per issuing warp (user tile) per CTA that reads the stage
     }
     // one full/empty pair per (accumulator stage, user tile): the groups of a user tile hand their
     // accumulator back without waiting for the other user tile's warps
@@ -453,34 +462,41 @@ score_topk_tc_kernel(const Params p) {
       for (int j = n_tiles > S ? n_tiles - S : 0; j < n_tiles; ++j)
         mbar_wait(bar_empty + 8 * (j % S), (j / S) & 1);
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      mbar_wait(bar_afull, 0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % S, a = j % NST;
-        mbar_wait(bar_full + 8 * s, (j / S) & 1);
-        tc_fence_after();
-        const uint64_t bdesc0 = make_desc(smem_u32(sB + (size_t)s * kBBytes), TN * 16, 128);
+  } else if (warp == 1 || (MT == 2 && warp == 3)) {
+    // ------------------------------------------------ MMA issuers: one WARP per user tile
+    // ncu of the round-1 kernel (profiles/r02_tc_topk_before_summary.txt): the epilogue warps sleep on
+    // the accumulator barrier on every tile and the single issuing THREAD is busy the whole time — ~250
+    // dependent instructions per item tile (runtime j % stages divisions, R2UR + ELECT + BRA.U.ANY around
+    // every UTCHMMA because the thread ran under `if (lane == 0)`), i.e. ~1100 clocks of issue latency
+    // for 512 clocks of tensor work.  Now: the whole warp runs the loop (uniform control flow, operands
+    // stay in uniform registers), stage / phase counters are carried instead of divided, descriptors
+    // are hoisted, and the two user tiles have their own issuing warp.
+    const int mt = warp == 1 ? 0 : 1;
+    mbar_wait(bar_afull, 0);
+    uint64_t adesc[kKSteps];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          if (j >= NST) {
-            mbar_wait(bar_tempty + 8 * (a * MT + mt), ((j / NST) - 1) & 1);
-            tc_fence_after();
-          }
-          const uint64_t adesc0 = make_desc(smem_u32(sA + (size_t)mt * kABytes), kUM * 16, 128);
+    for (int kk = 0; kk < kKSteps; ++kk)   // one K=16 step = two 16-byte k-chunks = 2*LBO bytes further along
+      adesc[kk] = make_desc(smem_u32(sA + (size_t)mt * kABytes), kUM * 16, 128) + (uint64_t)((kk * 2 * kUM * 16) >> 4);
+    const uint64_t bdesc_base = make_desc(smem_u32(sB), TN * 16, 128);
+    int s = 0, a = 0;
+    uint32_t full_parity = 0, acc_round = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(bar_full + 8 * s, full_parity);
+      if (acc_round > 0) mbar_wait(bar_tempty + 8 * (a * MT + mt), (acc_round - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bdesc0 = bdesc_base + (uint64_t)(((uint32_t)s * kBBytes) >> 4);
+        const uint32_t tacc = tmem_base + (uint32_t)((a * MT + mt) * TN);
 #pragma unroll
-          for (int kk = 0; kk < kKSteps; ++kk) {
-            // one K=16 step = two 16-byte k-chunks = 2*LBO bytes further along
-            const uint64_t ad = adesc0 + (uint64_t)((kk * 2 * kUM * 16) >> 4);
-            const uint64_t bd = bdesc0 + (uint64_t)((kk * 2 * TN * 16) >> 4);
-            tc_mma_bf16(tmem_base + (a * MT + mt) * TN, ad, bd, kIdesc, kk > 0 ? 1u : 0u);
-          }
-          tc_commit(bar_tfull + 8 * (a * MT + mt));   // this user tile's accumulator is ready for its groups
-        }
-        // smem stage reusable once these MMAs retire — in every CTA that received the tile
+        for (int kk = 0; kk < kKSteps; ++kk)
+          tc_mma_bf16(tacc, adesc[kk], bdesc0 + (uint64_t)((kk * 2 * TN * 16) >> 4), kIdesc, kk > 0 ? 1u : 0u);
+        tc_commit(bar_tfull + 8 * (a * MT + mt));   // this user tile's accumulator is ready for its groups
+        // smem stage reusable once the MMAs of BOTH issuers retire — in every CTA that received the tile
         if constexpr (CL > 1) tc_commit_mc(bar_empty + 8 * s, kClusterMask); else tc_commit(bar_empty + 8 * s);
       }
+      __syncwarp();
+      if (++s == S) { s = 0; full_parity ^= 1u; }
+      if (++a == NST) { a = 0; ++acc_round; }
     }
   } else if (warp >= kFrontWarps) {
     // ------------------------------------------------ epilogue: thread == user row
@@ -503,7 +519,9 @@ score_topk_tc_kernel(const Params p) {
     float* mv = cval + t;
     int* mi = cidx + t;
     Sel sel;
-    sel.thr = (live && p.debug_mode < 3) ? -INFINITY : INFINITY;   // debug 3: max tree only, no candidate ever passes
+    const int dbg = p.debug_mode;   // read once: the parameter load does not belong in the per-chunk loop
+    const int n_chunks_dbg = dbg == 1 ? 0 : 1;
+    sel.thr = (live && dbg < 3) ? -INFINITY : INFINITY;   // debug 3: max tree only, no candidate ever passes
     sel.cnt = 0;
     sel.sorted = 0;
     // warp-synchronous compaction once any lane holds k + 6 entries (at most cap - 4): folding early
@@ -601,7 +619,7 @@ score_topk_tc_kernel(const Params p) {
       const int item_tile0 = j * TN + c0 * COLS;
       const uint32_t tbase = tmem_base + lane_base + (uint32_t)((a * MT + mt) * TN + c0 * COLS);
 #pragma unroll 1
-      for (int cc = 0; cc < (p.debug_mode == 1 ? 0 : CPG); ++cc) {
+      for (int cc = 0; cc < CPG * n_chunks_dbg; ++cc) {
         uint32_t r[32], r2[32];
         __syncwarp();
         if (ACC16) {
@@ -611,7 +629,7 @@ score_topk_tc_kernel(const Params p) {
           tc_ld32(tbase + (uint32_t)(cc * COLS + 32), r2);
         }
         tc_wait_ld();
-        if (p.debug_mode == 2) {   // pipeline experiment: TMEM reads only, no selection work
+        if (dbg == 2) {   // pipeline experiment: TMEM reads only, no selection work
           if ((r[0] ^ r[31] ^ (ACC16 ? 0u : r2[0] ^ r2[31])) == 0x7fc12345u) sel.cnt = 1;
           continue;
         }

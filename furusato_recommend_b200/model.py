@@ -384,15 +384,30 @@ class LightGCN(nn.Module):
         lr = self.optim.param_groups[0]["lr"]
         if self._graph is None or self._graph_key != self._step_graph_key(B):
             self._capture_step_graph(B)
-        for dst, src in zip(self._gbatch, (users, pos, neg)):
-            dst.copy_(src, non_blocking=True)      # device slice or pinned host memory
+        if not (users.is_cuda or pos.is_cuda or neg.is_cuda):
+            # host triples (trainer.py:63 style callers): gather the three id arrays in ONE pinned staging
+            # buffer and ship them with one H2D copy instead of three
+            if self._hstage_ev is not None:
+                self._hstage_ev.synchronize()      # the previous step's copy has left the staging buffer
+            for k, src in enumerate((users, pos, neg)):
+                self._hstage[k].copy_(src)
+            self._gbatch_all.copy_(self._hstage, non_blocking=True)
+            if self._hstage_ev is None:
+                self._hstage_ev = torch.cuda.Event()
+            self._hstage_ev.record()
+        else:
+            for dst, src in zip(self._gbatch, (users, pos, neg)):
+                dst.copy_(src, non_blocking=True)  # device slices
         self._ze(self.all_embedding.weight)        # the captured layer 0 reads ZE: make sure it is current
         self._graph.replay()
         self._eval_cache_valid = False
 
     def _capture_step_graph(self, B: int) -> None:
         dev = self.all_embedding.weight.device
-        self._gbatch = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(3)]
+        self._gbatch_all = torch.zeros((3, B), dtype=torch.int64, device=dev)
+        self._gbatch = [self._gbatch_all[k] for k in range(3)]
+        self._hstage = torch.zeros((3, B), dtype=torch.int64).pin_memory()
+        self._hstage_ev = None
         st = self.optim._init_state(self.all_embedding.weight)
         # the warm-up step below must not move the model: snapshot and restore every mutable buffer
         keep = [t.clone() for t in (self.all_embedding.weight.data, st["exp_avg"], st["exp_avg_sq"], st["step"], st["hp"],

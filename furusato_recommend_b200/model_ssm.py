@@ -6,7 +6,9 @@ softplus loss of model/lgcn.py:98-118, and `OneEpoch` (lgcnssm.py:135-153) batch
 global `neg_size`, so it raises NameError as shipped).  This class keeps exactly that arithmetic —
 so it inherits the BPR parity pins — with `neg_size` read from the config (default 256, cfg-4 of
 BASELINE.json), and adds the real sampled-softmax objective of SURVEY §9.7 as an opt-in
-(`config["ssm_true_softmax"]`), which has no reference arithmetic behind it (parity unpinned).
+(`config["ssm_true_softmax"]`), which has no reference arithmetic behind it (parity unpinned): its
+fused step runs on `lgcn_ssm_fwd_bwd` (csrc/ssm.cu) + the same Horner backward / Adam epilogue as BPR;
+`_true_softmax_loss` is the plain-torch statement of the same formula that the kernel is tested against.
 """
 from __future__ import annotations
 
@@ -53,13 +55,43 @@ class LightGCNSSM(LightGCN):
         """lgcnssm.py:127-133."""
         if not self.true_softmax:
             return super().stageOne(user, pos, neg)
-        self.optim.zero_grad()
-        loss, reg = self._true_softmax_loss(user, pos, neg)
-        total = loss + float(self.config["decay"]) * reg
-        total.backward()
-        self.optim.step()
+        if self.config.get("ssm_autograd", False):   # the torch statement of the objective (tests)
+            self.optim.zero_grad()
+            loss, reg = self._true_softmax_loss(user, pos, neg)
+            total = loss + float(self.config["decay"]) * reg
+            total.backward()
+            self.optim.step()
+            self._eval_cache_valid = False
+            return total.detach()
+        with torch.no_grad():
+            self._fused_ssm_step(self._ids(user), self._ids(pos), self._ids(neg))
+            return self._buf("loss_out")[2].clone()
+
+    def _fused_ssm_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> None:
+        """Propagation, lgcn_ssm_fwd_bwd (loss + gradient seed), Adam tick, Horner backward with Adam in
+        the last epilogue — the fused BPR step with the loss kernel swapped."""
+        from . import ops
+        J = self.neg_size
+        w = self.all_embedding.weight
+        B = users.numel() // J
+        group = self.optim.param_groups[0]
+        st = self.optim._init_state(w)
+        out = self._buf("OUT")
+        self._propagate_into(w.data, out)
+        self._reset_seed_buffers()
+        G, cnt = self._buf("G"), self._buf("cnt")
+        decay = float(self.config["decay"])
+        ops.ssm_fwd_bwd(out, w.data, users, pos, neg, J, self.num_users, self.tau, decay, G, cnt, self._buf("loss_out"),
+                        self._work(B), self._buf("work_counter"))
+        ops.adam_tick(st["step"], st["hp"], group["lr"], group["betas"])
+        adam = dict(exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"], hp=st["hp"], betas=group["betas"],
+                    eps=group["eps"])
+        self._horner_into(G, grad_mode=2, reg_coef=decay / B, cnt=cnt, adam=adam)
+        if self.num_layers == 1:
+            G.zero_()
         self._eval_cache_valid = False
-        return total.detach()
+        if self.prescale_emb and self._col_scale is None:
+            self._ze_key = (w.data_ptr(), w._version)
 
     @torch.no_grad()
     def OneEpoch(self, user, pos, neg) -> torch.Tensor:
@@ -72,7 +104,7 @@ class LightGCNSSM(LightGCN):
             sl = slice(i, i + self._step_rows)
             if self.true_softmax:
                 with torch.enable_grad():
-                    aver = aver + self.stageOne(users[sl], pos[sl], neg[sl])
+                    aver = aver + self.stageOne(users[sl], pos[sl], neg[sl])   # fused kernel path unless ssm_autograd
             else:
                 self._fused_step_eager(users[sl], pos[sl], neg[sl])
                 aver = aver + self._buf("loss_out")[2]

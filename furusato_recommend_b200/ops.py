@@ -208,6 +208,27 @@ def zero_rows(table: torch.Tensor, ids: torch.Tensor) -> None:
                                       _chk(ids, torch.int64, "ids"), ids.numel(), st), "lgcn_zero_rows")
 
 
+def ssm_fwd_bwd(out: torch.Tensor, emb: torch.Tensor, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor,
+                n_neg: int, n_users: int, tau: float, decay: float, G: torch.Tensor, cnt: torch.Tensor,
+                loss_out: torch.Tensor, work: torch.Tensor, work_counter: torch.Tensor, loss_scale: float = 1.0) -> None:
+    """lgcn_ssm_fwd_bwd on flat triples (n_neg consecutive rows per (user, positive))."""
+    lib = _lib.load()
+    rows = users.numel()
+    if rows % n_neg or pos.numel() != rows or neg.numel() != rows:
+        raise ValueError(f"flat triples must hold a multiple of n_neg={n_neg} rows")
+    B = rows // n_neg
+    N, d = out.shape
+    if work.numel() < 2 * B or work_counter.numel() < 2:
+        raise ValueError("work must hold 2*B floats, work_counter 2 ints")
+    with _on(out, emb, users, pos, neg, G, cnt, loss_out, work, work_counter) as st:
+        _lib.check(lib.lgcn_ssm_fwd_bwd(
+            _chk(out, torch.float32, "out"), _chk(emb, torch.float32, "emb"),
+            _chk(users, torch.int64, "users"), _chk(pos, torch.int64, "pos"), _chk(neg, torch.int64, "neg"),
+            B, n_neg, n_users, N, d, tau, decay, loss_scale, _chk(G, torch.float32, "G"), _chk(cnt, torch.int32, "cnt"),
+            _chk(loss_out, torch.float32, "loss_out"), _chk(work, torch.float32, "work"),
+            _chk(work_counter, torch.int32, "work_counter"), st), "lgcn_ssm_fwd_bwd")
+
+
 def adam_tick(step: torch.Tensor, hp: torch.Tensor, lr: float, betas=(0.9, 0.999)) -> None:
     lib = _lib.load()
     with _on(step, hp) as st:

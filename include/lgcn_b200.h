@@ -212,6 +212,24 @@ int lgcn_bpr_fwd_bwd_rows(const float* rows, const int64_t* padded_ids, int64_t 
                           float* work, int32_t* work_counter, lgcn_stream_t stream);
 int lgcn_zero_rows(float* table, int d, const int64_t* ids, int64_t n_ids, lgcn_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Sampled-softmax forward + backward seed (BASELINE configs[3]).  PARITY UNPINNED: the
+ * reference's model/lgcnssm.py:98-118 `softmax_loss` is the BPR softplus loss and its OneEpoch raises
+ * NameError (:141); only the batch layout is the reference's — flat triples, n_neg consecutive rows
+ * per (user, positive): users[b*n_neg], pos[b*n_neg], neg[b*n_neg + j].  Specification (ours):
+ *   z_0 = <out[u], out[n+pos]>/tau, z_j = <out[u], out[n+neg_j]>/tau,  w = softmax(z_0..z_J)
+ *   loss_out[0] = mean_b[logsumexp(z) - z_0]
+ *   loss_out[1] = 0.5 * sum_b(|E[u]|^2 + |E[n+pos]|^2 + sum_j |E[n+neg_j]|^2) / B
+ *   loss_out[2] = [0] + decay * [1];  loss_out[3] += [2]
+ *   G[u] += c (sum_k w_k row_k - out[n+pos]); G[n+pos] += c (w_0 - 1) out[u]; G[n+neg_j] += c w_j out[u],
+ *   c = loss_scale / (tau * B); cnt[row] += 1 per occurrence.
+ * batch = number of (user, positive) pairs B.  work: float[2*B]; work_counter as lgcn_bpr_fwd_bwd.
+ * ------------------------------------------------------------------------ */
+int lgcn_ssm_fwd_bwd(const float* out, const float* emb, const int64_t* users, const int64_t* pos,
+                     const int64_t* neg, int64_t batch, int n_neg, int64_t n_users, int64_t n_nodes, int d,
+                     float tau, float decay, float loss_scale, float* G, int32_t* cnt, float* loss_out,
+                     float* work, int32_t* work_counter, lgcn_stream_t stream);
+
 /* Adam bookkeeping: ++(*step) and adam_hp = {lr / (1-beta1^t), sqrt(1-beta2^t)}
  * in double precision like torch.optim.Adam's Python scalars. */
 int lgcn_adam_tick(int64_t* step, float* adam_hp, double lr, double beta1, double beta2,
