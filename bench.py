@@ -409,7 +409,7 @@ def time_spmm_launches(model, step, n_steps: int, flush):
 
 
 def roofline_block(nnz_loc: int, n_loc: int, d: int, s_bytes: int, spmm_avg_s: float, K: int, table_bytes: float,
-                   traffic_key: str) -> dict:
+                   traffic_key: str, world_share: float = 1.0) -> dict:
     hbm_peak, _, _, which = measured_peaks()
     layer_bytes = spmm_layer_bytes(nnz_loc, n_loc, d, s_bytes)
     achieved = layer_bytes / spmm_avg_s / 1e9
@@ -433,6 +433,9 @@ def roofline_block(nnz_loc: int, n_loc: int, d: int, s_bytes: int, spmm_avg_s: f
            "note": ("SURVEY 8d gather model; the table is %.0f MB" % (table_bytes / 1e6)) +
                    (" — L2-resident: the gathered rows never reach DRAM, `frac` is NOT an HBM fraction here (see "
                     "dram_frac and the cfg3 block)" if l2_resident else " (>> 126 MB L2): HBM-bound")}
+    if traffic and world_share != 1.0:
+        traffic = traffic * world_share     # the capture is of the whole graph on one GPU
+        out["traffic"] = traffic
     if traffic:
         out["dram_gbs"] = traffic / spmm_avg_s / 1e9
         out["dram_frac"] = traffic / spmm_avg_s / 1e9 / hbm_peak
@@ -682,7 +685,8 @@ def run_cfg3_block(args, rank: int, world: int, local_rank: int) -> dict:
                    "h2d_bytes_per_step": 3 * B * 8, "d2h_bytes_per_step": 4},
            "gpu_launches": r["launches_per_step"] * steps,
            "roofline": roofline_block(nnz // world, N // world, d, s_bytes, r["spmm_avg_s"], K, N * d * s_bytes,
-                                      f"{'cfg3' if args.cfg3_shape == 'cfg3' else 'hbm'}_dram_bytes_per_launch_{args.storage}"),
+                                      f"{'cfg3' if args.cfg3_shape == 'cfg3' else 'hbm'}_dram_bytes_per_launch_{args.storage}",
+                                      world_share=1.0 / world),
            "parity": par, "setup_s": t_build,
            "l2": "table %.1f GB >> 126 MB L2; the 256 MiB flush is still written between timed steps" % (N * d * s_bytes / 1e9)}
     if world > 1:
@@ -884,7 +888,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         tag = {'hbm': 'hbm-bound', 'cfg3': 'cfg-3', 'cfg2': 'cfg-2',
                'cfg4': 'cfg-4 (lgcnssm, %d negatives per positive)' % J}[args.workload]
         roof2 = roofline_block(nnz // world, N // world, d, s_bytes, spmm_avg_s, K, N * d * s_bytes / world,
-                               f"{args.workload}_dram_bytes_per_launch_{args.storage}")
+                               f"{args.workload}_dram_bytes_per_launch_{args.storage}" if world == 1 else "none")
         out = {
             "metric": METRIC, "value": float(nnz) * K / (t_dev / args.steps), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,

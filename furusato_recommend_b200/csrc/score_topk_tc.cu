@@ -60,6 +60,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// accumulator hand-off waits (epilogue <-> MMA issuers): the suspend-time hint is a tuning knob
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  if (mbar_try_wait_hint(bar, parity, hint_ns)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, hint_ns)) {
+    if ((++spins & 0xfffffu) == 0 && clock64() - t0 > 8000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   // the last operand is a suspend-time hint: a waiting thread sleeps in hardware instead of
@@ -357,6 +377,7 @@ struct Params {
                            // 2 = TMEM reads only, 3 = reads + max tree, no candidate passes
   int acc16;               // 1: f16 accumulators, read back two per register (tcgen05.ld pack::16b)
   int split;               // bulk copies per item tile (tuning: LGCN_TC_SPLIT)
+  uint32_t wait_hint;      // suspend-time hint (ns) of the accumulator hand-off waits (tuning: LGCN_TC_WAIT_NS)
 };
 
 // MT user tiles (128 rows each) share every item tile: the B operand stream is what bounds the MMA
@@ -482,7 +503,7 @@ score_topk_tc_kernel(const Params p) {
     uint32_t full_parity = 0, acc_round = 0;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(bar_full + 8 * s, full_parity);
-      if (acc_round > 0) mbar_wait(bar_tempty + 8 * (a * MT + mt), (acc_round - 1) & 1);
+      if (acc_round > 0) mbar_wait_hint(bar_tempty + 8 * (a * MT + mt), (acc_round - 1) & 1, p.wait_hint);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bdesc0 = bdesc_base + (uint64_t)(((uint32_t)s * kBBytes) >> 4);
@@ -546,7 +567,7 @@ score_topk_tc_kernel(const Params p) {
     if constexpr (RS) {
       for (int j = 0; j < n_tiles; ++j) {
         const int a = j % NST;
-        mbar_wait(bar_tfull + 8 * (a * MT + mt), (j / NST) & 1);
+        mbar_wait_hint(bar_tfull + 8 * (a * MT + mt), (j / NST) & 1, p.wait_hint);
         tc_fence_after();
         const uint32_t tbase = tmem_base + lane_base + (uint32_t)((a * MT + mt) * TN);
         uint32_t r[4][32];
@@ -614,7 +635,7 @@ score_topk_tc_kernel(const Params p) {
 #endif
     for (int j = 0; j < n_tiles; ++j) {
       const int a = j % NST;
-      mbar_wait(bar_tfull + 8 * (a * MT + mt), (j / NST) & 1);
+      mbar_wait_hint(bar_tfull + 8 * (a * MT + mt), (j / NST) & 1, p.wait_hint);
       tc_fence_after();
       const int item_tile0 = j * TN + c0 * COLS;
       const uint32_t tbase = tmem_base + lane_base + (uint32_t)((a * MT + mt) * TN + c0 * COLS);
@@ -787,6 +808,7 @@ constexpr size_t kSmemLimit = 227 * 1024;
 // launch of the process, never on the per-launch path.
 struct Tuning {
   int debug_mode, trig, split, stages;
+  uint32_t wait_hint;
   std::string layout;
 };
 static const Tuning& tuning() {
@@ -801,6 +823,8 @@ static const Tuning& tuning() {
     if (x.split != 1 && x.split != 2 && x.split != 4 && x.split != 8) x.split = 1;
     const char* sg = getenv("LGCN_TC_STAGES");
     x.stages = sg ? atoi(sg) : 0;
+    const char* wh = getenv("LGCN_TC_WAIT_NS");
+    x.wait_hint = wh ? (uint32_t)atoll(wh) : 0x989680u;
     const char* le = getenv("LGCN_TC_LAYOUT");
     x.layout = le ? le : "auto";
     return x;
@@ -912,6 +936,7 @@ static int run_cfg(const float* user_emb, const float* item_emb, const int64_t* 
   p.debug_mode = tuning().debug_mode;
   p.trig = tuning().trig;
   p.split = tuning().split;
+  p.wait_hint = tuning().wait_hint;
   return launch<D, TN, GROUPS, MT, NST, RS, CL>(p, st);
 }
 
@@ -939,6 +964,7 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
 #if LGCN_TC_RS
       if (layout == "m2rs") return run_cfg<D, 128, 2, 2, 2, true>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
 #endif
+      if (layout == "m2s4") return run_cfg<D, 64, 2, 2, 4>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);   // 4 TMEM stages x 64 columns
       if (layout == "m2c2") return run_cfg<D, 128, 2, 2, 2, false, 2>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
       if (layout == "m2c4") return run_cfg<D, 128, 2, 2, 2, false, 4>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
       if (layout == "m2g2" || layout == "auto") return run_cfg<D, 128, 2, 2, 2>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
