@@ -693,6 +693,19 @@ def run_cfg3_block(args, rank: int, world: int, local_rank: int) -> dict:
         out["parallelism"] = (f"{world} GPUs, {'side_split' if getattr(model.part, 'side_split', False) else 'two_sided'} "
                               f"partition, exchange={model.exchange}; roofline bytes are the rank-local share "
                               "(peer stores of the fused all-gather not counted)")
+    if args.storage == "fp32" and not args.no_bf16_block:
+        # the same graph with the activations stored / exchanged as bf16 (fp32 accumulate): halves the gathered
+        # bytes and, at N > 1, the NVLink volume of the fused all-gather
+        del model
+        r["model"] = None
+        gc.collect(); torch.cuda.empty_cache()
+        rb = measure_train(args, W, ds, dict(cfg, storage_dtype="bf16"), rank, world, dev, steps, warmup, n, m)
+        out["bf16_storage"] = {"ms_per_step": rb["t_dev"] / steps * 1e3, "value": nnz * K / (rb["t_dev"] / steps), "unit": UNIT,
+                               "spmm_avg_launch_us": rb["spmm_avg_s"] * 1e6,
+                               "parity": eigen_parity(rb["model"], ds, world, rank, dev),
+                               "what": "activations stored / exchanged as bf16, fp32 accumulate; tolerance 2e-2"}
+        model = rb["model"]
+        del rb
     del model, r, ds, tu, ti, su, si
     gc.collect()
     torch.cuda.empty_cache()

@@ -93,8 +93,17 @@ class CsrGraph:
         return self._struct
 
 
-def decompose_rows(rowptr: torch.Tensor, hub_deg: int = _lib.HUB_DEG, seg_edges: int = _lib.SEG_EDGES):
-    """Light rows (degree-descending) and CTA segments of the hub rows."""
+def decompose_rows(rowptr: torch.Tensor, hub_deg: int = _lib.HUB_DEG, seg_edges: int = _lib.SEG_EDGES,
+                   interleave: int = 0):
+    """Light rows (degree-descending) and CTA segments of the hub rows.
+
+    `interleave` > 0 (row-partitioned graphs whose SpMM epilogue pushes every output row to the peers):
+    the degree-sorted light rows are cut into chunks of `interleave` rows and the chunks are dealt
+    heaviest, lightest, 2nd heaviest, 2nd lightest, ...  A purely degree-descending order finishes
+    few rows per microsecond at the start of the launch and very many at the end, so the NVLink
+    stores of the fused all-gather pile up in the tail; with the interleaved order the bytes pushed
+    per edge processed are roughly constant over the launch and the exchange hides behind the gather.
+    Rows of one chunk (a few CTAs) still have similar degrees, so warps stay balanced."""
     dev = rowptr.device
     deg = rowptr[1:] - rowptr[:-1]
     n = deg.numel()
@@ -102,7 +111,18 @@ def decompose_rows(rowptr: torch.Tensor, hub_deg: int = _lib.HUB_DEG, seg_edges:
     sdeg = deg[order]
     n_hub = int((sdeg > hub_deg).sum())
     hub_rows = order[:n_hub]
-    light_rows = order[n_hub:].to(torch.int32)
+    light_rows = order[n_hub:]
+    if interleave > 0 and light_rows.numel() > 2 * interleave:
+        n_l = light_rows.numel()
+        n_chunks = (n_l + interleave - 1) // interleave
+        c = torch.arange(n_chunks, device=dev)
+        half = (n_chunks + 1) // 2
+        chunk_order = torch.empty(n_chunks, dtype=torch.int64, device=dev)
+        chunk_order[0::2] = c[:half]                                   # heaviest first ...
+        chunk_order[1::2] = torch.flip(c[half:], dims=(0,))            # ... alternating with the lightest
+        pos = (chunk_order[:, None] * interleave + torch.arange(interleave, device=dev)[None, :]).reshape(-1)
+        light_rows = light_rows[pos[pos < n_l]]
+    light_rows = light_rows.to(torch.int32)
     hub_deg_t = sdeg[:n_hub]
     hub_nseg = (hub_deg_t + seg_edges - 1) // seg_edges
     hub_seg0 = torch.cumsum(hub_nseg, 0) - hub_nseg

@@ -345,7 +345,10 @@ class DistLightGCN:
             mode_p = "side_split" if max(self.n, self.m) <= 2 * min(self.n, self.m) else "two_sided"
         self.part = RowPartition(g.rowptr, world, n_users=self.n, side_split=(mode_p == "side_split"))
         rp, colp, dl = self.part.local_csr(rank, g.rowptr, g.col, g.dinv)
-        self.local_graph = CsrGraph(self.part.rows[rank], 0, rp, colp, dl, **decompose_rows(rp))
+        # the push exchange stores every output row to the peers from the SpMM epilogue: interleave heavy and
+        # light row chunks so those stores are spread over the launch (graph.decompose_rows)
+        self.local_graph = CsrGraph(self.part.rows[rank], 0, rp, colp, dl,
+                                    **decompose_rows(rp, interleave=int(config.get("dist_row_interleave", 32))))
         self.local_nnz = int(colp.numel())
         R, d, dev = self.part.R, self.d, self.device
         gen = torch.Generator(device=dev).manual_seed(seed + rank)

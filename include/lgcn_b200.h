@@ -11,8 +11,11 @@
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller unless it says HOST;
  *     outputs are pre-allocated by the caller; no allocation happens inside;
- *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*),
- *     stateless and re-entrant; it can be captured into a CUDA graph;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*) and can be
+ *     captured into a CUDA graph.  The library keeps no state of its own, but some ARGUMENTS are
+ *     mutable scratch the caller owns — `hub_counter` / `partial` inside lgcn_graph_t, `work` /
+ *     `work_counter` of the loss kernels: launches that share them must be stream-ordered (two
+ *     streams on ONE lgcn_graph_t race; give each stream its own scratch);
  *   - return value: 0 = ok, > 0 = a cudaError_t, < 0 = LGCN_ERR_*; the message is
  *     available from lgcn_last_error() (thread-local).  Nothing throws.
  *   - embedding rows are row-major [N, d] with users first, then items
