@@ -71,6 +71,9 @@ def parse():
                          "cfg4: configs[3], LightGCNSSM 4-layer d=64, 256 negatives per positive on the same graph; "
                          "cfg5: configs[4], full-rank top-20 eval of --eval-users users x 2M items, user-sharded")
     ap.add_argument("--eval-users", type=int, default=1_000_000, help="cfg5: users scored (all ranks together)")
+    ap.add_argument("--ssm-softmax", action="store_true",
+                    help="cfg4: the true sampled-softmax objective on lgcn_ssm_fwd_bwd (parity unpinned) instead of the "
+                         "reference's own arithmetic for model/lgcnssm.py (BPR over neg_size*B flat triples)")
     return ap.parse_args()
 
 
@@ -899,7 +902,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         s_bytes = 2 if args.storage == "bf16" else 4
         ms = t_dev / args.steps * 1e3
         tag = {'hbm': 'hbm-bound', 'cfg3': 'cfg-3', 'cfg2': 'cfg-2',
-               'cfg4': 'cfg-4 (lgcnssm, %d negatives per positive)' % J}[args.workload]
+               'cfg4': 'cfg-4 (lgcnssm, %d negatives per positive%s)' % (J, ', true sampled softmax' if args.ssm_softmax else '')}[args.workload]
         roof2 = roofline_block(nnz // world, N // world, d, s_bytes, spmm_avg_s, K, N * d * s_bytes / world,
                                f"{args.workload}_dram_bytes_per_launch_{args.storage}" if world == 1 else "none")
         out = {
@@ -997,8 +1000,10 @@ def measure_cfg4(args, W: dict, ds, cfg: dict, dev: str):
     from furusato_recommend_b200 import LightGCNSSM, UniformSample
     J, K, B = int(W["neg_size"]), W["layers"], W["batch"] * int(W["neg_size"])
     cfg["neg_size"] = J
-    model = LightGCNSSM(cfg, ds)   # reference arithmetic: the BPR softplus over J*B flat triples per step
+    cfg["ssm_true_softmax"] = bool(args.ssm_softmax)
+    model = LightGCNSSM(cfg, ds)   # default = reference arithmetic: the BPR softplus over J*B flat triples per step
     model.train()
+    fused = model._fused_ssm_step if args.ssm_softmax else model._fused_step
     S = UniformSample(ds, neg_ratio=J, seed=CFG2["seed"], epoch=0, count=(B // J) * 4)
     n_batches = len(S) // B
     users, pos, neg = (S[:, j].contiguous() for j in range(3))
@@ -1006,7 +1011,7 @@ def measure_cfg4(args, W: dict, ds, cfg: dict, dev: str):
 
     def step(i):
         b = (i % n_batches) * B
-        model._fused_step(users[b:b + B], pos[b:b + B], neg[b:b + B])
+        fused(users[b:b + B], pos[b:b + B], neg[b:b + B])
 
     for i in range(args.warmup):
         step(i)
