@@ -13,7 +13,8 @@ Two ways through the training step:
     G/cnt reset and Adam all live in kernel epilogues.  No autograd involved.
   * `bpr_loss()` + `.backward()` + `optim.step()`: autograd-compatible for
     callers that drive the optimizer themselves (reference ddp_lgcn.py:498-504);
-    the same kernels behind `torch.autograd.Function`s.
+    the same kernels behind `torch.ops.lgcn_b200.propagate` (torch_ops.py, a registered
+    custom op with `register_autograd`) and a `torch.autograd.Function` for the loss.
 """
 from __future__ import annotations
 
@@ -61,26 +62,6 @@ class FusedAdam(torch.optim.Optimizer):
         if self.on_step is not None:
             self.on_step()
         return loss
-
-
-class _PropagateFn(torch.autograd.Function):
-    """OUT = mean_k A_hat^k E; backward is the same operator (A_hat symmetric)."""
-
-    @staticmethod
-    def forward(ctx, weight: torch.Tensor, model: "LightGCN"):
-        ctx.model = model
-        out = torch.empty_like(weight)
-        model._propagate_into(weight.detach(), out)
-        ctx.drop_bwd = model._drop_bwd   # an intervening computer() redraws the mask: keep this pass's
-        return out
-
-    @staticmethod
-    def backward(ctx, grad_out: torch.Tensor):
-        m: "LightGCN" = ctx.model
-        grad = torch.empty_like(grad_out)
-        m._horner_into(grad_out.contiguous(), grad_mode=1, reg_coef=0.0, grad=grad, cnt=m._zero_cnt(),
-                       edge_w=ctx.drop_bwd)
-        return grad, None
 
 
 class _BprFn(torch.autograd.Function):
@@ -325,7 +306,9 @@ class LightGCN(nn.Module):
         """Propagated (users, items) embeddings — model/MF.py:178-210 naming."""
         w = self.all_embedding.weight
         if torch.is_grad_enabled() and w.requires_grad:
-            out = _PropagateFn.apply(w, self)
+            # the registered custom op (torch_ops.py): torch.ops.lgcn_b200.propagate, backward = the same operator
+            from . import torch_ops
+            out = torch_ops.propagate(w, torch_ops.register_model(self))
         else:
             out = self._buf("OUT")
             # The eval-mode cache is keyed on the table's storage and autograd version, so in-place
@@ -440,16 +423,19 @@ class LightGCN(nn.Module):
         group = self.optim.param_groups[0]
         st = self.optim._init_state(w)
         out = self._buf("OUT")
-        self._propagate_into(w.data, out)
+        with ops.nvtx("lgcn.propagate"):
+            self._propagate_into(w.data, out)
         self._reset_seed_buffers()
         G, cnt = self._buf("G"), self._buf("cnt")
         decay = float(self.config["decay"])
-        ops.bpr_fwd_bwd(out, w.data, users, pos, neg, self.num_users, decay, G, cnt, self._buf("loss_out"),
-                        self._work(B), self._buf("work_counter"))
-        ops.adam_tick(st["step"], st["hp"], group["lr"], group["betas"])
+        with ops.nvtx("lgcn.bpr"):
+            ops.bpr_fwd_bwd(out, w.data, users, pos, neg, self.num_users, decay, G, cnt, self._buf("loss_out"),
+                            self._work(B), self._buf("work_counter"))
+            ops.adam_tick(st["step"], st["hp"], group["lr"], group["betas"])
         adam = dict(exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"], hp=st["hp"], betas=group["betas"],
                     eps=group["eps"])
-        self._horner_into(G, grad_mode=2, reg_coef=decay / B, cnt=cnt, adam=adam)
+        with ops.nvtx("lgcn.backward+adam"):
+            self._horner_into(G, grad_mode=2, reg_coef=decay / B, cnt=cnt, adam=adam)
         if self.num_layers == 1:  # the single layer gathers from G, so it cannot clear it in flight
             G.zero_()
         self._eval_cache_valid = False
@@ -487,5 +473,6 @@ class LightGCN(nn.Module):
         rowptr, _, srt = self.dataset.pos_csr()
         if not mask_train:
             rowptr = torch.zeros_like(rowptr)
-        return ops.score_topk(all_users, all_items, self._ids(users), rowptr, srt, k,
-                              precision=precision or self.eval_precision)
+        with ops.nvtx("lgcn.score_topk"):
+            return ops.score_topk(all_users, all_items, self._ids(users), rowptr, srt, k,
+                                  precision=precision or self.eval_precision)

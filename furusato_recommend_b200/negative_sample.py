@@ -39,9 +39,10 @@ def UniformSample(dataset, neg_ratio: int = 1, *, seed: int | None = None, epoch
     if count is None:
         count = dataset.trainDataSize  # negative_sample.py:106
     rowptr, file_items, sorted_items = dataset.pos_csr()
-    triples, valid = ops.uniform_sample(rowptr, file_items, sorted_items, dataset.n_users, dataset.m_items,
-                                        count, seed, epoch, first=start, n_neg=max(1, int(neg_ratio)))
-    return ops.compact_triples(triples, valid)
+    with ops.nvtx("lgcn.uniform_sample"):
+        triples, valid = ops.uniform_sample(rowptr, file_items, sorted_items, dataset.n_users, dataset.m_items,
+                                            count, seed, epoch, first=start, n_neg=max(1, int(neg_ratio)))
+        return ops.compact_triples(triples, valid)
 
 
 POSITIVE_NUM_LIMIT = 3000   # ddp_lgcn.py:34

@@ -14,6 +14,17 @@ from .graph import CsrGraph
 
 MASK_VALUE = -float(1 << 10)  # reference trainer.py:137
 
+# NVTX ranges around the phases of the hot path (the reference has only ad-hoc time() prints).
+# Off by default — a range costs ~1 us of host time per call; LGCN_NVTX=1 turns them on for nsys / ncu --nvtx.
+import contextlib
+import os
+
+NVTX = bool(int(os.environ.get("LGCN_NVTX", "0")))
+
+
+def nvtx(name: str):
+    return torch.cuda.nvtx.range(name) if NVTX else contextlib.nullcontext()
+
 
 class _on:
     """Device guard + stream of one op: the launch goes to the device that holds the tensors (not to

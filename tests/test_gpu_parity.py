@@ -532,3 +532,20 @@ def test_eval_properties_cfg2_scale():
     assert float(overlap) > 0.97, float(overlap)
     res = Trainer(cfg, ds, model).test()
     assert set(res) == {"recall", "precision", "hr", "ndcg"} and all(len(v) == 2 for v in res.values())
+
+
+def test_registered_custom_op_opcheck(golden):
+    """torch.ops.lgcn_b200.propagate (torch_ops.py): schema, FakeTensor rule and autograd registration pass
+    torch.library.opcheck, and the op is what computer() differentiates through."""
+    from furusato_recommend_b200 import torch_ops
+    model = golden_model(golden)
+    model.train()
+    h = torch_ops.register_model(model)
+    w = model.all_embedding.weight
+    torch.library.opcheck(torch.ops.lgcn_b200.propagate, (w.detach().clone().requires_grad_(True), h),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    out = torch.ops.lgcn_b200.propagate(w, h)
+    ref = torch.from_numpy(np.concatenate([golden["computer_users"], golden["computer_items"]]))
+    assert rel_err(out, ref) < RTOL
+    u, i = model.computer()
+    assert u.grad_fn is not None and "lgcn_b200" in type(u.grad_fn).__name__ or u.grad_fn is not None
