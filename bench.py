@@ -694,7 +694,8 @@ def run_cfg3_block(args, rank: int, world: int, local_rank: int) -> dict:
            "l2": "table %.1f GB >> 126 MB L2; the 256 MiB flush is still written between timed steps" % (N * d * s_bytes / 1e9)}
     if world > 1:
         out["parallelism"] = (f"{world} GPUs, {'side_split' if getattr(model.part, 'side_split', False) else 'two_sided'} "
-                              f"partition, exchange={model.exchange}; roofline bytes are the rank-local share "
+                              f"partition, exchange={model.exchange}"
+                              f"{' (NVSwitch multicast stores)' if getattr(model.prop, 'mcast', [0])[0] else ''}; roofline bytes are the rank-local share "
                               "(peer stores of the fused all-gather not counted)")
     if args.storage == "fp32" and not args.no_bf16_block:
         # the same graph with the activations stored / exchanged as bf16 (fp32 accumulate): halves the gathered

@@ -12,7 +12,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("LGCN_B200_LIB", PKG / "liblgcn_b200.so"))  # override: tuning variants
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 F32, BF16, F16 = 0, 1, 2
 HUB_DEG = 256
 SEG_EDGES = 1024
@@ -51,7 +51,7 @@ class LayerArgs(C.Structure):
         ("zero_base", C.c_int),
         ("n_dst_peers", C.c_int), ("dst_row_offset", C.c_int64), ("dst_peers", C.c_void_p * MAX_PEERS),
         ("src_scale", C.c_void_p), ("dst_scale", C.c_void_p), ("edge_w", C.c_void_p),
-        ("push_emb", C.c_int),
+        ("push_emb", C.c_int), ("dst_multicast", C.c_void_p),
     ]
 
 

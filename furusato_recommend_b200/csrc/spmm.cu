@@ -102,6 +102,7 @@ struct EpiDev {
   int n_peer;
   int64_t dst_row_off;
   void* peer[LGCN_MAX_PEERS];
+  void* mc;   // multicast mapping of the gathered buffer (NVLS) or NULL
 };
 
 // Sum of w_j * SRC[col[e]] over e = e0, e0+1, .. inside [e0, e_end) taken in
@@ -223,6 +224,31 @@ __device__ __forceinline__ RowPre<EPL> row_prefetch(const EpiDev& p, int64_t row
 // goes to every reader's gathered buffer over NVLink (peer-mapped pointers), at this rank's row block.
 template <int D, int EPL, bool DST_BF16>
 __device__ __forceinline__ void store_dst_row(const EpiDev& p, int64_t row, int lig, const float (&z)[EPL]) {
+  if (p.mc != nullptr) {
+    // one store, replicated by the NVSwitch into every rank's gathered buffer
+    const int64_t moff = (p.dst_row_off + row) * D + lig * EPL;
+    if (DST_BF16) {
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.mc) + moff;
+      if (EPL == 8) {
+        asm volatile("multimem.st.weak.global.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dp), "r"(pack_bf16x2(z[0], z[1])),
+                     "r"(pack_bf16x2(z[2], z[3])), "r"(pack_bf16x2(z[4 % EPL], z[5 % EPL])),
+                     "r"(pack_bf16x2(z[6 % EPL], z[7 % EPL]))
+                     : "memory");
+      } else {
+        asm volatile("multimem.st.weak.global.v2.bf16x2 [%0], {%1, %2};" ::"l"(dp), "r"(pack_bf16x2(z[0], z[1])),
+                     "r"(pack_bf16x2(z[2], z[3]))
+                     : "memory");
+      }
+    } else {
+      float* dp = reinterpret_cast<float*>(p.mc) + moff;
+#pragma unroll
+      for (int qq = 0; qq < EPL / 4; ++qq)
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + 4 * qq), "f"(z[4 * qq]),
+                     "f"(z[4 * qq + 1]), "f"(z[4 * qq + 2]), "f"(z[4 * qq + 3])
+                     : "memory");
+    }
+    return;
+  }
   const int n_dst = p.n_peer > 0 ? p.n_peer : 1;
   const int64_t doff = p.n_peer > 0 ? (p.dst_row_off + row) * D + lig * EPL : row * D + lig * EPL;
   for (int q = 0; q < n_dst; ++q) {
@@ -588,6 +614,8 @@ extern "C" int lgcn_propagate_layer(const lgcn_graph_t* gh, const lgcn_layer_arg
   p.eps = (float)a->eps;
   p.zero_base = a->zero_base;
   p.push_emb = a->push_emb;
+  p.mc = a->dst_multicast;
+  LGCN_CHECK_ARG(a->dst_multicast == nullptr || a->dst != nullptr, "dst_multicast needs dst (it fixes the dtype)");
   LGCN_CHECK_ARG(!a->push_emb || (a->grad_mode == 2 && a->dst != nullptr), "push_emb needs grad_mode 2 and dst");
   LGCN_CHECK_ARG(a->n_dst_peers >= 0 && a->n_dst_peers <= LGCN_MAX_PEERS, "n_dst_peers out of range");
   p.n_peer = a->n_dst_peers;

@@ -80,7 +80,7 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
                     betas=(0.9, 0.999), eps: float = 1e-8, zero_base: bool = False,
                     dst_peers: Optional[Sequence[int]] = None, dst_row_offset: int = 0,
                     src_scale: Optional[torch.Tensor] = None, dst_scale: Optional[torch.Tensor] = None,
-                    edge_w: Optional[torch.Tensor] = None, push_emb: bool = False) -> None:
+                    edge_w: Optional[torch.Tensor] = None, push_emb: bool = False, dst_multicast: int = 0) -> None:
     """lgcn_propagate_layer: one normalised-adjacency SpMM + fused row epilogue.
     `src_scale` / `dst_scale` ([N] fp32) replace the graph's dinv on the column / row side
     (rAdjGCN's asymmetric normalisation); None keeps D^-1/2 A D^-1/2.  `edge_w` ([nnz] fp32) weights
@@ -109,6 +109,9 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
     a.beta1, a.beta2, a.eps = betas[0], betas[1], eps
     a.zero_base = int(zero_base)
     a.push_emb = int(push_emb)
+    a.dst_multicast = int(dst_multicast) or None
+    if dst_multicast:
+        a.dst_row_offset = dst_row_offset
     for t, nm in ((src_scale, "src_scale"), (dst_scale, "dst_scale")):
         if t is not None and (t.dim() != 1 or t.shape[0] < N):
             raise ValueError(f"{nm} must be [>={N}], got {tuple(t.shape)}")
@@ -123,7 +126,7 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
         a.n_dst_peers, a.dst_row_offset = len(dst_peers), dst_row_offset
         for i, ptr in enumerate(dst_peers):
             a.dst_peers[i] = ptr
-    for t, nm in ((None if dst_peers else dst, "dst"), (base, "base"), (acc_in, "acc_in"), (acc_out, "acc_out"), (emb, "emb"),
+    for t, nm in ((None if (dst_peers or dst_multicast) else dst, "dst"), (base, "base"), (acc_in, "acc_in"), (acc_out, "acc_out"), (emb, "emb"),
                   (grad, "grad"), (adam_m, "adam_m"), (adam_v, "adam_v")):
         if t is not None and (t.dim() != 2 or t.shape[0] < N or t.shape[1] != d):
             raise ValueError(f"{nm} must be [>={N}, {d}], got {tuple(t.shape)}")

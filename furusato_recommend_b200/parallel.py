@@ -246,7 +246,7 @@ class PushPropagator:
     (start of forward, after every non-final layer)."""
 
     def __init__(self, part: RowPartition, rank: int, graph, dinv_local: torch.Tensor, n_layers: int,
-                 ops, group, d: int, storage_dtype: torch.dtype, device):
+                 ops, group, d: int, storage_dtype: torch.dtype, device, use_multicast: bool = True):
         import torch.distributed._symmetric_memory as symm
         self.part, self.rank, self.K, self.ops, self.graph = part, rank, n_layers, ops, graph
         self.dinv, self.storage_dtype = dinv_local, storage_dtype
@@ -258,10 +258,22 @@ class PushPropagator:
         readers = part.readers_of(rank)   # side-split partition: only the other side's ranks
         self.peers = [[int(h.buffer_ptrs[r]) for r in readers] for h in self.hdl]
         self.row0 = rank * R
+        # NVSwitch multicast (NVLS): when every rank reads every row (two_sided partition) and the
+        # symmetric allocation has a multicast mapping, a row is stored ONCE and the switch replicates
+        # it into all W gathered buffers — per-rank NVLink egress per layer drops from W shards to one.
+        self.mcast = [0, 0]
+        if use_multicast and not part.side_split:
+            mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.hdl]
+            if all(mc):
+                self.mcast = mc
         self.x0_valid = False   # buf[0] holds dinv (.) E of the CURRENT table on every reader
 
     def _barrier(self):
         self.hdl[0].barrier(channel=0)
+
+    def _push_target(self, b: int) -> dict:
+        """Where the epilogue of a layer stores its rows for buffer b: the multicast mapping, or the readers' peer pointers."""
+        return dict(dst_multicast=self.mcast[b]) if self.mcast[b] else dict(dst_peers=self.peers[b])
 
     def push_x0(self, emb_local: torch.Tensor) -> None:
         """Explicit exchange of the pre-scaled table (first step, after load_global_embedding, after
@@ -279,8 +291,8 @@ class PushPropagator:
             last = k == K - 1
             nxt = (k + 1) & 1
             ops.propagate_layer(self.graph, self.bufs[k & 1], scale_src=False,
-                                dst=None if last else self.bufs[nxt],
-                                dst_peers=None if last else self.peers[nxt], dst_row_offset=self.row0,
+                                dst=None if last else self.bufs[nxt], dst_row_offset=self.row0,
+                                **({} if last else self._push_target(nxt)),
                                 acc_in=emb_local if k == 0 else acc, acc_out=out if last else acc,
                                 acc_scale=1.0 / (K + 1) if last else 1.0)
             if not last:
@@ -301,7 +313,7 @@ class PushPropagator:
             nxt = (a + j + 1) & 1
             kw = dict(last_kwargs, push_emb=True) if last else {}
             ops.propagate_layer(self.graph, g0_src if j == 0 else self.bufs[(a + j) & 1], scale_src=False,
-                                dst=self.bufs[nxt], dst_peers=self.peers[nxt], dst_row_offset=self.row0,
+                                dst=self.bufs[nxt], dst_row_offset=self.row0, **self._push_target(nxt),
                                 base=G_local, **kw)
             if not last:
                 self._barrier()
@@ -371,7 +383,8 @@ class DistLightGCN:
         if world > 1 and mode in ("auto", "push"):
             try:
                 self.prop = PushPropagator(self.part, rank, self.local_graph, dl, self.K, ops,
-                                           group if group is not None else dist.group.WORLD, d, storage, dev)
+                                           group if group is not None else dist.group.WORLD, d, storage, dev,
+                                           use_multicast=bool(config.get("dist_multicast", True)))
                 self.exchange = "push"
             except Exception as e:  # no P2P / symmetric memory on this box
                 if mode == "push":

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LGCN_ABI_VERSION 2
+#define LGCN_ABI_VERSION 3
 
 #define LGCN_ERR_INVALID_ARG (-1)
 #define LGCN_ERR_UNSUPPORTED (-2)
@@ -148,6 +148,11 @@ typedef struct lgcn_layer_args {
    * t_i.  The first layer of the next propagation then gathers it with scale_src = 0 (and, in the
    * row-partitioned case, needs no separate exchange of the updated table). */
   int push_emb;
+  /* NVSwitch multicast (NVLS) form of the fused all-gather: when non-NULL the dst row is written ONCE, with
+   * multimem.st, to row (dst_row_offset + i) of this multicast mapping — the switch replicates it into the
+   * gathered buffer of every rank of the mapping — instead of n_dst_peers unicast peer stores (the
+   * per-rank NVLink egress drops from n_dst_peers rows to one).  dst must still be non-NULL. */
+  void* dst_multicast;
 } lgcn_layer_args_t;
 
 int lgcn_propagate_layer(const lgcn_graph_t* g /*HOST*/, const lgcn_layer_args_t* a /*HOST*/,
