@@ -246,6 +246,11 @@ class LightGCN(nn.Module):
             raise IndexError(f"{bad} (user, pos, neg) sample(s) with an id outside [0, {self.num_users}) / "
                              f"[0, {self.num_items}) were skipped (reference: IndexError at model/lgcn.py:90-95)")
 
+    def check_ids(self) -> None:
+        """Raise the reference's IndexError (model/lgcn.py:90-95) if any step since the last call saw a
+        (user, pos, neg) id outside the table.  One host sync; OneEpoch and bpr_loss call it themselves."""
+        self._raise_on_bad_ids()
+
     def _check_host_ids(self, users, pos, neg) -> None:
         """Ids that arrive on the host are range-checked there (cheap), before anything is launched."""
         for t, hi, nm in ((users, self.num_users, "user"), (pos, self.num_items, "positive item"),
@@ -352,9 +357,10 @@ class LightGCN(nn.Module):
         """model/lgcn.py:127-133 as one fused step: zero_grad + bpr_loss +
         decay*reg + backward + Adam.  Returns loss + decay*reg (0-dim tensor)."""
         u, p, q = self._ids(user, keep_host=True), self._ids(pos, keep_host=True), self._ids(neg, keep_host=True)
-        self._check_host_ids(u, p, q)
+        if self.config.get("check_ids", False):   # six host reductions (~30 us): off on the hot path; the kernel
+            self._check_host_ids(u, p, q)         # skips and counts bad ids anyway and the loss comes back NaN
         self._fused_step(u, p, q)
-        return self._buf("loss_out")[2].clone()   # NaN if a device-side id was out of range (see OneEpoch)
+        return self._buf("loss_out")[2].clone()   # NaN if an id was out of range; check_ids() raises the IndexError
 
     def _fused_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor) -> None:
         """One fused train step.  Full-size batches replay a captured CUDA graph (8 kernels, no
