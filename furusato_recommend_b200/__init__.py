@@ -7,10 +7,10 @@ load the library; the first op does and fails loudly if it is missing.
 from .dataloader import BasicDataset, Loader  # noqa: F401
 from .model import FusedAdam, LightGCN  # noqa: F401
 from .model_ssm import LightGCNSSM  # noqa: F401
-from .model_variants import RGCN, rAdjGCN  # noqa: F401
+from .model_variants import DDPLightGCN, RGCN, rAdjGCN  # noqa: F401
 from .negative_sample import UniformSample, UniformSampleCapped, UniformSampling, set_seed  # noqa: F401
 from .trainer import Trainer, minibatch, shuffle  # noqa: F401
 
-__all__ = ["BasicDataset", "Loader", "LightGCN", "LightGCNSSM", "rAdjGCN", "RGCN", "FusedAdam", "UniformSample",
+__all__ = ["BasicDataset", "Loader", "LightGCN", "LightGCNSSM", "rAdjGCN", "RGCN", "DDPLightGCN", "FusedAdam", "UniformSample",
            "UniformSampleCapped", "UniformSampling", "set_seed", "Trainer",
            "minibatch", "shuffle"]

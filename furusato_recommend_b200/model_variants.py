@@ -10,6 +10,10 @@
   purchase lists only.  `relation_emb` (:86) is created but never read by forward(), as in the
   reference.
 
+* `DDPLightGCN` — the inline model of ddp_lgcn.py:406-538, whose call shape differs from model/lgcn.py:
+  `forward(edge_index)`, `stageOne(optimizer, u, p, n)` / `OneEpoch(optimizer, u, p, n)` with a
+  caller-owned optimizer (ddp_lgcn.py:664,673), and `getUsersRating() -> (user_x, item_x)` (:535-538).
+
 Everything else (bpr_loss, stageOne, OneEpoch, getUsersRating, getUsersTopK, the fused step and
 its CUDA graph) is inherited from `LightGCN`.
 """
@@ -60,3 +64,63 @@ class RGCN(LightGCN):
         self.purchaseSize, self.favoriteSize = 2 * len(dataset.trainUser), 2 * len(fu)   # rgcn.py:58,81
         return build_csr_graph(dataset.n_users, dataset.m_items, torch.from_numpy(u).to(dev),
                                torch.from_numpy(i).to(dev))
+
+
+class DDPLightGCN(LightGCN):
+    """The call shape of ddp_lgcn.py's inline `LightGCN` (SURVEY §8b "DDP shape"), for launchers that wrap
+    the model in `DistributedDataParallel(model).module` and own the optimizer.
+
+    The reference builds both `edge_index` (train edges) and `inference_edge_index`
+    (dataset.inferenceUser / inferenceItem, ddp_lgcn.py:427-441) and only ever propagates over the
+    latter (getEmbedding :471, getUsersRating :537): the graph here is built from the inference
+    edges when the dataset has them, from the train edges otherwise.  `forward(edge_index)` accepts
+    and ignores the argument — the CSR graph was built once, and re-deriving `gcn_norm` from an
+    edge list on every call is exactly the work the reference's LGConv wastes.
+
+    With a caller-owned optimizer the step is bpr_loss -> backward -> optimizer.step(), i.e. the
+    autograd path through `torch.ops.lgcn_b200.propagate`; pass the model's own `optim` (FusedAdam)
+    to get the fused single-graph step instead."""
+
+    def _build_graph(self, dataset) -> CsrGraph:
+        iu, ii = getattr(dataset, "inferenceUser", None), getattr(dataset, "inferenceItem", None)
+        if iu is None or ii is None:
+            return dataset.csr_graph()
+        dev = torch.device(self.config.get("device", "cuda:0"))
+        return build_csr_graph(dataset.n_users, dataset.m_items, torch.as_tensor(np.asarray(iu, dtype=np.int64)).to(dev),
+                               torch.as_tensor(np.asarray(ii, dtype=np.int64)).to(dev))
+
+    def forward(self, edge_index=None):
+        """ddp_lgcn.py:466-474"""
+        return self.computer()
+
+    def stageOne(self, optimizer, user, pos, neg) -> torch.Tensor:
+        """ddp_lgcn.py:498-504"""
+        if optimizer is self.optim:
+            return super().stageOne(user, pos, neg)
+        with torch.enable_grad():
+            optimizer.zero_grad()
+            loss, reg_loss = self.bpr_loss(user, pos, neg)
+            loss = loss + float(self.config["decay"]) * reg_loss
+            loss.backward()
+            optimizer.step()
+        self._invalidate_derived()
+        return loss.detach()
+
+    def OneEpoch(self, optimizer, user, pos, neg) -> torch.Tensor:
+        """ddp_lgcn.py:506-523: contiguous mini-batches, loss sum / (len // B + 1)."""
+        if optimizer is self.optim:
+            return super().OneEpoch(user, pos, neg)
+        users, pos, neg = self._ids(user), self._ids(pos), self._ids(neg)
+        B = int(self.config["bpr_batch_size"])
+        aver = torch.zeros((), device=users.device)
+        for i in range(0, len(users), B):
+            aver = aver + self.stageOne(optimizer, users[i:i + B], pos[i:i + B], neg[i:i + B])
+        return aver / (len(users) // B + 1)
+
+    @torch.no_grad()
+    def getUsersRating(self, users=None):
+        """ddp_lgcn.py:535-538 returns the propagated (user_x, item_x) tables (the launcher does the batched
+        matmul / mask / top-k itself, :690-711); with `users` given, the dense scores of model/lgcn.py:120-125."""
+        if users is None:
+            return self.computer()
+        return super().getUsersRating(users)

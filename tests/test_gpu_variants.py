@@ -163,3 +163,27 @@ def test_edge_dropout_matches_live_reference(golden, variants, storage):
     assert np.isfinite(l1) and np.isfinite(l2) and not torch.equal(w1, model._drop_fwd)
     frac = float((model._drop_fwd > 0).float().mean())
     assert abs(frac - keep) < 0.05
+
+
+def test_ddp_shaped_model_with_a_caller_owned_optimizer(golden):
+    """ddp_lgcn.py's call shape (forward(edge_index), OneEpoch(optimizer, ...), getUsersRating() -> tables) with
+    a stock torch.optim.Adam the caller owns (ddp_lgcn.py:664): two steps reproduce the live reference's golden
+    losses and table (autograd through torch.ops.lgcn_b200.propagate), and the model's own FusedAdam takes the
+    fused path with the same result."""
+    from furusato_recommend_b200 import DDPLightGCN
+    cfg = _cfg(golden)
+    bu, bp, bn = batch(golden)
+    for own in (False, True):
+        model = _load(DDPLightGCN(cfg, golden_dataset(golden)), golden).train()
+        opt = model.optim if own else torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+        l1 = model.stageOne(opt, bu, bp, bn)
+        l2 = model.stageOne(opt, bu, bp, bn)
+        for l, key in ((l1, "step1_loss"), (l2, "step2_loss")):
+            assert abs(float(l) - float(golden[key])) <= 1e-5 * abs(float(golden[key])), (own, key)
+        assert float((model.all_embedding.weight.detach().cpu() - torch.from_numpy(golden["E2"])).abs().max()) < 2e-6
+        model.eval()
+        ux, ix = model.getUsersRating()                      # (user_x, item_x), ddp_lgcn.py:535-538
+        fu, fi = model.forward(None)                         # edge_index accepted and ignored
+        assert ux.shape == (int(golden["n_users"]), cfg["recdim"]) and torch.equal(ux, fu) and torch.equal(ix, fi)
+        ep = model.train().OneEpoch(opt, bu.repeat(3)[:150], bp.repeat(3)[:150], bn.repeat(3)[:150])
+        assert torch.isfinite(ep)
