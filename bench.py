@@ -604,7 +604,12 @@ def measure_train(args, W: dict, ds, cfg: dict, rank: int, world: int, dev: str,
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
         clk = clocks.stop()
+    spmm_ranks = None
     if world > 1:
+        mine = torch.tensor([spmm_avg_s], device=dev, dtype=torch.float64)
+        allr = torch.zeros(world, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        spmm_ranks = [round(float(x) * 1e6, 1) for x in allr]     # per-rank average SpMM launch (us): the skew a layer barrier waits for
         t = torch.tensor([t_dev, t_e2e, spmm_avg_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e, spmm_avg_s = (float(x) for x in t)
@@ -612,7 +617,7 @@ def measure_train(args, W: dict, ds, cfg: dict, rank: int, world: int, dev: str,
         parity = parity_vs_oracle(model, ds, W, (users[:B], pos[:B], neg[:B]))
     return dict(model=model, nnz=nnz, t_dev=t_dev, t_e2e=t_e2e, spmm_avg_s=spmm_avg_s, steps=steps,
                 launches_per_step=launches_per_step, clocks=clk, parity=parity, sampler=sampler, flush=flush,
-                batch=(users[:B], pos[:B], neg[:B]))
+                batch=(users[:B], pos[:B], neg[:B]), spmm_ranks=spmm_ranks)
 
 
 def eigen_parity(model, ds, world: int, rank: int, dev: str) -> dict:
@@ -693,6 +698,7 @@ def run_cfg3_block(args, rank: int, world: int, local_rank: int) -> dict:
            "parity": par, "setup_s": t_build,
            "l2": "table %.1f GB >> 126 MB L2; the 256 MiB flush is still written between timed steps" % (N * d * s_bytes / 1e9)}
     if world > 1:
+        out["spmm_avg_launch_us_per_rank"] = r.get("spmm_ranks")
         out["parallelism"] = (f"{world} GPUs, {'side_split' if getattr(model.part, 'side_split', False) else 'two_sided'} "
                               f"partition, exchange={model.exchange}"
                               f"{' (NVSwitch multicast stores)' if getattr(model.prop, 'mcast', [0])[0] else ''}; roofline bytes are the rank-local share "
