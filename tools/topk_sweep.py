@@ -24,7 +24,10 @@ ue = torch.randn(a.users, a.d, generator=g, device=dev) * 0.1
 ie = torch.randn(a.items, a.d, generator=g, device=dev) * 0.1
 ids = torch.arange(a.users, device=dev)
 rp = torch.arange(a.users + 1, device=dev, dtype=torch.int64) * a.npos
-pos = torch.sort(torch.randint(0, a.items, (a.users, a.npos), generator=g, device=dev, dtype=torch.int32), dim=1)[0].reshape(-1).contiguous()
+if a.npos > 0:
+    pos = torch.sort(torch.randint(0, a.items, (a.users, a.npos), generator=g, device=dev, dtype=torch.int32), dim=1)[0].reshape(-1).contiguous()
+else:   # no masked positives at all (isolates the cost of the positives walk)
+    pos = torch.zeros(1, dtype=torch.int32, device=dev)
 ops.score_topk(ue, ie, ids, rp, pos, a.k, precision=a.precision)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
