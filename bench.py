@@ -62,7 +62,7 @@ def parse():
                     help="graph of the cfg3 block: cfg3 = BASELINE configs[2]; hbm = 2.4M x 0.6M x 60M edges (quick)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "push", "nccl"],
                     help="N>1: push = all-gather fused into the SpMM epilogue over NVLink peer memory")
-    ap.add_argument("--partition", default="auto", choices=["auto", "side_split", "two_sided"],
+    ap.add_argument("--partition", default="auto", choices=["auto", "side_split", "two_sided", "reduce"],
                     help="N>1: side_split = users on the first N/2 ranks, items on the rest (a row is only sent to "
                          "the other side); two_sided = every rank owns 1/N of both sides")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "hbm", "cfg3", "cfg4", "cfg5"],
@@ -699,7 +699,7 @@ def run_cfg3_block(args, rank: int, world: int, local_rank: int) -> dict:
            "l2": "table %.1f GB >> 126 MB L2; the 256 MiB flush is still written between timed steps" % (N * d * s_bytes / 1e9)}
     if world > 1:
         out["spmm_avg_launch_us_per_rank"] = r.get("spmm_ranks")
-        out["parallelism"] = (f"{world} GPUs, {'side_split' if getattr(model.part, 'side_split', False) else 'two_sided'} "
+        out["parallelism"] = (f"{world} GPUs, {'reduce (user rows never travel)' if getattr(model, 'reduce_mode', False) else ('side_split' if getattr(model.part, 'side_split', False) else 'two_sided')} "
                               f"partition, exchange={model.exchange}"
                               f"{' (NVSwitch multicast stores)' if getattr(model.prop, 'mcast', [0])[0] else ''}; roofline bytes are the rank-local share "
                               "(peer stores of the fused all-gather not counted)")
@@ -777,7 +777,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     flush = r["flush"]
     launches_per_step, clk, sampler_info, parity_info = r["launches_per_step"], r["clocks"], r["sampler"], r["parity"]
     exch = getattr(model, "exchange", None)
-    partn = None if world == 1 else ("side_split" if getattr(model.part, "side_split", False) else "two_sided")
+    partn = None if world == 1 else ("reduce" if getattr(model, "reduce_mode", False) else
+                                     ("side_split" if getattr(model.part, "side_split", False) else "two_sided"))
 
     def barrier():
         if world > 1:

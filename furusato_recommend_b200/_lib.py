@@ -12,7 +12,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("LGCN_B200_LIB", PKG / "liblgcn_b200.so"))  # override: tuning variants
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 F32, BF16, F16 = 0, 1, 2
 HUB_DEG = 256
 SEG_EDGES = 1024
@@ -51,7 +51,7 @@ class LayerArgs(C.Structure):
         ("zero_base", C.c_int),
         ("n_dst_peers", C.c_int), ("dst_row_offset", C.c_int64), ("dst_peers", C.c_void_p * MAX_PEERS),
         ("src_scale", C.c_void_p), ("dst_scale", C.c_void_p), ("edge_w", C.c_void_p),
-        ("push_emb", C.c_int), ("dst_multicast", C.c_void_p),
+        ("push_emb", C.c_int), ("dst_multicast", C.c_void_p), ("dst_route_rows", C.c_int64),
     ]
 
 
@@ -61,6 +61,7 @@ SIGNATURES = {
     "lgcn_abi_version": (C.c_int, []),
     "lgcn_last_error": (C.c_char_p, []),
     "lgcn_propagate_layer": (C.c_int, [C.POINTER(GraphStruct), C.POINTER(LayerArgs), _P]),
+    "lgcn_reduce_rows": (C.c_int, [_P, _I, _I64, _I64, _P, C.POINTER(LayerArgs), _P]),
     "lgcn_scale_rows_push": (C.c_int, [_P, _P, _I64, _I, _I, C.POINTER(C.c_void_p), _I, _I64, _P]),
     "lgcn_exchange_rows_push": (C.c_int, [_P, _P, _I, _P, _I64, _I64, _I, C.POINTER(C.c_void_p), _I, _P]),
     "lgcn_bpr_fwd_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _F, _F, _P, _P, _P, _P, _P, _P]),

@@ -103,6 +103,7 @@ struct EpiDev {
   int64_t dst_row_off;
   void* peer[LGCN_MAX_PEERS];
   void* mc;   // multicast mapping of the gathered buffer (NVLS) or NULL
+  int64_t route_rows;  // > 0: row i goes to peer[i / route_rows] only, at row dst_row_off + i % route_rows
 };
 
 // Sum of w_j * SRC[col[e]] over e = e0, e0+1, .. inside [e0, e_end) taken in
@@ -249,10 +250,14 @@ __device__ __forceinline__ void store_dst_row(const EpiDev& p, int64_t row, int 
     }
     return;
   }
-  const int n_dst = p.n_peer > 0 ? p.n_peer : 1;
-  const int64_t doff = p.n_peer > 0 ? (p.dst_row_off + row) * D + lig * EPL : row * D + lig * EPL;
+  // route_rows: every row has ONE destination, the peer that owns it (partial sums of the reduce partition)
+  const bool routed = p.route_rows > 0 && p.n_peer > 0;
+  const int q_routed = routed ? (int)(row / p.route_rows) : 0;
+  const int64_t row_d = routed ? row - (int64_t)q_routed * p.route_rows : row;
+  const int n_dst = routed ? 1 : (p.n_peer > 0 ? p.n_peer : 1);
+  const int64_t doff = p.n_peer > 0 ? (p.dst_row_off + row_d) * D + lig * EPL : row * D + lig * EPL;
   for (int q = 0; q < n_dst; ++q) {
-    void* base_ptr = p.n_peer > 0 ? p.peer[q] : p.dst;
+    void* base_ptr = p.n_peer > 0 ? p.peer[routed ? q_routed : q] : p.dst;
     if (DST_BF16) {
       __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(base_ptr) + doff;
       if (EPL == 8) {
@@ -475,7 +480,9 @@ static int dispatch_dtype(const lgcn_layer_args_t* a, const GraphDev& g, const E
   if (!sb && !db) return dispatch_wmode<D, false, false>(wmode, g, p, st);
   if (!sb && db) return dispatch_wmode<D, false, true>(wmode, g, p, st);
   if (sb && db) return dispatch_wmode<D, true, true>(wmode, g, p, st);
-  set_last_error("bf16 source with fp32 destination is not a LightGCN layer");
+  // bf16 source, fp32 destination: raw fp32 partial sums of a bf16-stored activation (reduce partition)
+  if (wmode == 0) return launch_layer<D, true, false, 0>(g, p, st);
+  set_last_error("a bf16 source with an fp32 destination supports neither scale_src nor edge_w");
   return LGCN_ERR_UNSUPPORTED;
 }
 
@@ -575,6 +582,10 @@ extern "C" int lgcn_exchange_rows_push(const float* tab_a, const float* tab_b, i
 extern "C" int lgcn_abi_version(void) { return LGCN_ABI_VERSION; }
 extern "C" const char* lgcn_last_error(void) { return lgcn::last_error(); }
 
+namespace lgcn {
+static int fill_epilogue(const lgcn_layer_args_t* a, const float* dinv, EpiDev& p);
+}
+
 extern "C" int lgcn_propagate_layer(const lgcn_graph_t* gh, const lgcn_layer_args_t* a,
                                     lgcn_stream_t stream) {
   LGCN_CHECK_ARG(gh != nullptr && a != nullptr, "null graph/args");
@@ -600,9 +611,25 @@ extern "C" int lgcn_propagate_layer(const lgcn_graph_t* gh, const lgcn_layer_arg
   g.partial = gh->partial;
 
   EpiDev p;
+  if (int rc = fill_epilogue(a, gh->dinv, p)) return rc;
+
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->d) {
+    case 32: return dispatch_dtype<32>(a, g, p, st);
+    case 64: return dispatch_dtype<64>(a, g, p, st);
+    case 128: return dispatch_dtype<128>(a, g, p, st);
+    default:
+      set_last_error("unsupported embedding width d=%d (supported: 32, 64, 128)", a->d);
+      return LGCN_ERR_UNSUPPORTED;
+  }
+}
+
+namespace lgcn {
+// lgcn_layer_args_t -> the epilogue parameter block both kernels use
+static int fill_epilogue(const lgcn_layer_args_t* a, const float* dinv, EpiDev& p) {
   p.edge_w = a->edge_w;
-  p.src_scale = a->src_scale != nullptr ? a->src_scale : gh->dinv;
-  p.dst_scale = a->dst_scale != nullptr ? a->dst_scale : gh->dinv;
+  p.src_scale = a->src_scale != nullptr ? a->src_scale : dinv;
+  p.dst_scale = a->dst_scale != nullptr ? a->dst_scale : dinv;
   p.src = a->src; p.dst = a->dst; p.base = a->base;
   p.acc_in = a->acc_in; p.acc_out = a->acc_out; p.acc_scale = a->acc_scale;
   p.grad_mode = a->grad_mode; p.inv_layers = a->inv_layers; p.reg_coef = a->reg_coef;
@@ -621,15 +648,69 @@ extern "C" int lgcn_propagate_layer(const lgcn_graph_t* gh, const lgcn_layer_arg
   p.n_peer = a->n_dst_peers;
   p.dst_row_off = a->dst_row_offset;
   for (int q = 0; q < LGCN_MAX_PEERS; ++q) p.peer[q] = q < a->n_dst_peers ? a->dst_peers[q] : nullptr;
+  p.route_rows = a->dst_route_rows;
+  LGCN_CHECK_ARG(a->dst_route_rows >= 0 && (a->dst_route_rows == 0 || a->n_dst_peers > 0), "dst_route_rows needs dst_peers");
   LGCN_CHECK_ARG(!(a->zero_base && a->base == a->src), "zero_base with src == base races");
+  return 0;
+}
 
+// Owner-side half of the reduce partition: s_i = sum_q partials[q][i] (fixed order: deterministic), then the
+// SAME row epilogue as the SpMM (x_i = dst_scale_i * s_i, layer sum, next layer's pre-scaled row pushed to the
+// readers, Horner base, Adam).  One group of D/4 lanes per row, 16 bytes per lane.
+template <int D, bool DST_BF16>
+__global__ void __launch_bounds__(kBlock)
+reduce_rows_kernel(const float* __restrict__ partials, int n_parts, int64_t part_rows, int64_t n_rows, const EpiDev p) {
+  constexpr int LPR = D / 4, NG = kBlock / LPR;
+  const int lig = threadIdx.x % LPR;
+  const int64_t row = (int64_t)blockIdx.x * NG + threadIdx.x / LPR;
+  if (row >= n_rows) return;
+  const unsigned gmask = group_mask(LPR);
+  const RowPre<4> pre = row_prefetch<D, 4>(p, row, lig);
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int q = 0; q < n_parts; ++q) {
+    const float4 v = ldg_f4_stream(partials + ((int64_t)q * part_rows + row) * D + lig * 4);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+  }
+  row_epilogue<D, 4, DST_BF16>(p, pre, row, lig, gmask, s);
+}
+}  // namespace lgcn
+
+extern "C" int lgcn_reduce_rows(const float* partials, int n_parts, int64_t part_rows, int64_t n_rows, const float* dinv,
+                                const lgcn_layer_args_t* a, lgcn_stream_t stream) {
+  LGCN_CHECK_ARG(partials != nullptr && dinv != nullptr && a != nullptr, "null pointer argument");
+  LGCN_CHECK_ARG(n_parts >= 1 && n_parts <= LGCN_MAX_PEERS && part_rows >= n_rows && n_rows >= 0, "bad shape");
+  LGCN_CHECK_ARG(a->acc_out == nullptr || a->acc_in != nullptr, "acc_out needs acc_in");
+  LGCN_CHECK_ARG(a->grad_mode >= 0 && a->grad_mode <= 2, "grad_mode must be 0, 1 or 2");
+  if (a->grad_mode != 0) {
+    LGCN_CHECK_ARG(a->emb != nullptr && a->cnt != nullptr, "grad_mode needs emb and cnt");
+    LGCN_CHECK_ARG(a->grad_mode != 1 || a->grad != nullptr, "grad_mode 1 needs grad");
+    LGCN_CHECK_ARG(a->grad_mode != 2 || (a->adam_m && a->adam_v && a->adam_hp && a->base),
+                   "grad_mode 2 needs adam_m, adam_v, adam_hp and base");
+  }
+  if (n_rows == 0) return 0;
+  lgcn::EpiDev p;
+  if (int rc = lgcn::fill_epilogue(a, dinv, p)) return rc;
+  p.src = partials;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool db = a->dst != nullptr && a->dst_dtype == LGCN_BF16;
+#define LGCN_REDUCE(D_)                                                                                     \
+  case D_: {                                                                                                \
+    constexpr int NG = lgcn::kBlock / (D_ / 4);                                                             \
+    const unsigned grid = (unsigned)((n_rows + NG - 1) / NG);                                               \
+    if (db) lgcn::reduce_rows_kernel<D_, true><<<grid, lgcn::kBlock, 0, st>>>(partials, n_parts, part_rows, n_rows, p); \
+    else lgcn::reduce_rows_kernel<D_, false><<<grid, lgcn::kBlock, 0, st>>>(partials, n_parts, part_rows, n_rows, p);   \
+    break;                                                                                                  \
+  }
   switch (a->d) {
-    case 32: return dispatch_dtype<32>(a, g, p, st);
-    case 64: return dispatch_dtype<64>(a, g, p, st);
-    case 128: return dispatch_dtype<128>(a, g, p, st);
+    LGCN_REDUCE(32)
+    LGCN_REDUCE(64)
+    LGCN_REDUCE(128)
     default:
       set_last_error("unsupported embedding width d=%d (supported: 32, 64, 128)", a->d);
       return LGCN_ERR_UNSUPPORTED;
   }
+#undef LGCN_REDUCE
+  LGCN_LAUNCH_OK();
+  return 0;
 }
+

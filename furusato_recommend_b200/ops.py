@@ -70,30 +70,25 @@ def _dt(t: torch.Tensor) -> int:
     raise TypeError(f"unsupported storage dtype {t.dtype}")
 
 
-def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Optional[torch.Tensor] = None,
-                    base: Optional[torch.Tensor] = None, acc_in: Optional[torch.Tensor] = None,
-                    acc_out: Optional[torch.Tensor] = None, acc_scale: float = 1.0,
-                    grad_mode: int = 0, inv_layers: float = 1.0, reg_coef: float = 0.0,
-                    cnt: Optional[torch.Tensor] = None, emb: Optional[torch.Tensor] = None,
-                    grad: Optional[torch.Tensor] = None, adam_m: Optional[torch.Tensor] = None,
-                    adam_v: Optional[torch.Tensor] = None, adam_hp: Optional[torch.Tensor] = None,
-                    betas=(0.9, 0.999), eps: float = 1e-8, zero_base: bool = False,
-                    dst_peers: Optional[Sequence[int]] = None, dst_row_offset: int = 0,
-                    src_scale: Optional[torch.Tensor] = None, dst_scale: Optional[torch.Tensor] = None,
-                    edge_w: Optional[torch.Tensor] = None, push_emb: bool = False, dst_multicast: int = 0) -> None:
-    """lgcn_propagate_layer: one normalised-adjacency SpMM + fused row epilogue.
-    `src_scale` / `dst_scale` ([N] fp32) replace the graph's dinv on the column / row side
-    (rAdjGCN's asymmetric normalisation); None keeps D^-1/2 A D^-1/2.  `edge_w` ([nnz] fp32) weights
-    every CSR slot (edge dropout)."""
-    lib = _lib.load()
-    n_src, d = src.shape
-    N = g.n_nodes  # rows of this (possibly rank-local) graph; src may hold more rows (all-gathered)
-    if n_src < N:
-        raise ValueError(f"src has {n_src} rows, graph has {N} nodes")
+def _layer_args(N: int, d: int, src: Optional[torch.Tensor], *, scale_src: bool = False,
+                dst: Optional[torch.Tensor] = None,
+                base: Optional[torch.Tensor] = None, acc_in: Optional[torch.Tensor] = None,
+                acc_out: Optional[torch.Tensor] = None, acc_scale: float = 1.0,
+                grad_mode: int = 0, inv_layers: float = 1.0, reg_coef: float = 0.0,
+                cnt: Optional[torch.Tensor] = None, emb: Optional[torch.Tensor] = None,
+                grad: Optional[torch.Tensor] = None, adam_m: Optional[torch.Tensor] = None,
+                adam_v: Optional[torch.Tensor] = None, adam_hp: Optional[torch.Tensor] = None,
+                betas=(0.9, 0.999), eps: float = 1e-8, zero_base: bool = False,
+                dst_peers: Optional[Sequence[int]] = None, dst_row_offset: int = 0,
+                src_scale: Optional[torch.Tensor] = None, dst_scale: Optional[torch.Tensor] = None,
+                edge_w: Optional[torch.Tensor] = None, nnz: int = 0, push_emb: bool = False, dst_multicast: int = 0,
+                dst_route_rows: int = 0) -> "_lib.LayerArgs":
+    """lgcn_layer_args_t for N output rows of width d (shared by lgcn_propagate_layer and lgcn_reduce_rows)."""
     a = _lib.LayerArgs()
-    a.d, a.src_dtype, a.scale_src = d, _dt(src), int(scale_src)
-    a.dst_dtype = _dt(dst) if dst is not None else _dt(src)
-    a.src = _chk(src, src.dtype, "src")
+    a.d, a.scale_src = d, int(scale_src)
+    a.src_dtype = _dt(src) if src is not None else _lib.F32
+    a.dst_dtype = _dt(dst) if dst is not None else a.src_dtype
+    a.src = _chk(src, src.dtype, "src") if src is not None else 0
     a.dst = _chk(dst, dst.dtype, "dst") if dst is not None else 0
     a.base = _chk(base, torch.float32, "base", True)
     a.acc_in = _chk(acc_in, torch.float32, "acc_in", True)
@@ -110,6 +105,7 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
     a.zero_base = int(zero_base)
     a.push_emb = int(push_emb)
     a.dst_multicast = int(dst_multicast) or None
+    a.dst_route_rows = int(dst_route_rows)
     if dst_multicast:
         a.dst_row_offset = dst_row_offset
     for t, nm in ((src_scale, "src_scale"), (dst_scale, "dst_scale")):
@@ -117,8 +113,8 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
             raise ValueError(f"{nm} must be [>={N}], got {tuple(t.shape)}")
     a.src_scale = _chk(src_scale, torch.float32, "src_scale", True)
     a.dst_scale = _chk(dst_scale, torch.float32, "dst_scale", True)
-    if edge_w is not None and (edge_w.dim() != 1 or edge_w.numel() != g.nnz):
-        raise ValueError(f"edge_w must be [{g.nnz}] (one weight per CSR slot), got {tuple(edge_w.shape)}")
+    if edge_w is not None and (edge_w.dim() != 1 or edge_w.numel() != nnz):
+        raise ValueError(f"edge_w must be [{nnz}] (one weight per CSR slot), got {tuple(edge_w.shape)}")
     a.edge_w = _chk(edge_w, torch.float32, "edge_w", True)
     if dst_peers:
         if dst is None:
@@ -130,8 +126,40 @@ def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, dst: Opt
                   (grad, "grad"), (adam_m, "adam_m"), (adam_v, "adam_v")):
         if t is not None and (t.dim() != 2 or t.shape[0] < N or t.shape[1] != d):
             raise ValueError(f"{nm} must be [>={N}, {d}], got {tuple(t.shape)}")
-    with _on(src, dst, base, acc_in, acc_out, emb, grad, adam_m, adam_v, g.col) as st:
+    return a
+
+
+def propagate_layer(g: CsrGraph, src: torch.Tensor, *, scale_src: bool, n_src_rows: int = 0, **kw) -> None:
+    """lgcn_propagate_layer: one normalised-adjacency SpMM + fused row epilogue (keyword arguments:
+    `_layer_args`).  `src_scale` / `dst_scale` ([N] fp32) replace the graph's dinv on the column / row side
+    (rAdjGCN's asymmetric normalisation); None keeps D^-1/2 A D^-1/2.  `edge_w` ([nnz] fp32) weights
+    every CSR slot (edge dropout).  `n_src_rows`: for a rectangular local graph (rows and columns are different
+    node sets) the number of rows `src` must hold; by default the graph's own row count."""
+    lib = _lib.load()
+    n_src, d = src.shape
+    N = g.n_nodes  # rows of this (possibly rank-local) graph; src may hold more rows (all-gathered)
+    if n_src < (n_src_rows or N):
+        raise ValueError(f"src has {n_src} rows, the graph's columns reach {n_src_rows or N}")
+    a = _layer_args(N, d, src, scale_src=scale_src, nnz=g.nnz, **kw)
+    with _on(src, kw.get("dst"), kw.get("base"), kw.get("acc_in"), kw.get("acc_out"), kw.get("emb"), kw.get("grad"),
+             kw.get("adam_m"), kw.get("adam_v"), g.col) as st:
         _lib.check(lib.lgcn_propagate_layer(C.byref(g.c_struct(d)), C.byref(a), st), "lgcn_propagate_layer")
+
+
+def reduce_rows(partials: torch.Tensor, n_rows: int, dinv: torch.Tensor, **kw) -> None:
+    """lgcn_reduce_rows: s_i = sum_q partials[q, i] for i < n_rows, then lgcn_propagate_layer's row epilogue
+    (keyword arguments: `_layer_args`) — the owner-side half of the reduce partition."""
+    lib = _lib.load()
+    if partials.dim() != 3 or partials.dtype != torch.float32 or partials.shape[1] < n_rows:
+        raise ValueError("partials must be fp32 [n_parts, >= n_rows, d]")
+    n_parts, part_rows, d = partials.shape
+    if dinv.dim() != 1 or dinv.shape[0] < n_rows:
+        raise ValueError("dinv must cover the reduced rows")
+    a = _layer_args(n_rows, d, None, **kw)
+    with _on(partials, dinv, kw.get("dst"), kw.get("base"), kw.get("acc_in"), kw.get("acc_out"), kw.get("emb"),
+             kw.get("adam_m"), kw.get("adam_v")) as st:
+        _lib.check(lib.lgcn_reduce_rows(_chk(partials, torch.float32, "partials"), n_parts, part_rows, n_rows,
+                                        _chk(dinv, torch.float32, "dinv"), C.byref(a), st), "lgcn_reduce_rows")
 
 
 def scale_rows_push(x: torch.Tensor, dinv: torch.Tensor, dst_dtype: torch.dtype, dst_peers: Sequence[int],

@@ -320,6 +320,159 @@ class PushPropagator:
         self.x0_valid = True
 
 
+def reduce_local_graphs(part: RowPartition, rank: int, rowptr: torch.Tensor, col: torch.Tensor):
+    """The two local CSRs of the "reduce" partition (two-sided RowPartition of a bipartite graph).
+
+    A  rows = this rank's users (local order), columns = PADDED ids of their items: the user rows gather
+       from the gathered item table exactly like the all-gather partition does.
+    B  rows = ALL items in owner-block numbering b * R_i + j (R_i = largest item block; padding rows are
+       empty), columns = LOCAL index of this rank's users: the partial sum of every item over the users
+       that live here; block b of the rows belongs to rank b.
+    Returns (rowptr_A, col_A, rowptr_B, col_B, R_i, item_rows_per_rank)."""
+    dev = rowptr.device
+    W = part.world
+    (u_lo, u_hi), (i_lo, i_hi) = part.ranges(rank)
+    # ---- A
+    e0, e1 = int(rowptr[u_lo]), int(rowptr[u_hi])
+    rp_a = (rowptr[u_lo:u_hi + 1] - e0).contiguous()
+    col_a = part.to_padded(col[e0:e1].to(torch.int64)).to(torch.int32).contiguous()
+    # ---- B: every item row, neighbours restricted to [u_lo, u_hi)
+    item_cuts = part.cuts[1]                                  # [W + 1] global item-row boundaries
+    n_first, n_last = int(item_cuts[0]), int(item_cuts[-1])
+    sizes = (item_cuts[1:] - item_cuts[:-1])
+    R_i = max(int(sizes.max()), 1)
+    f0, f1 = int(rowptr[n_first]), int(rowptr[n_last])
+    deg = rowptr[n_first + 1:n_last + 1] - rowptr[n_first:n_last]
+    row_of = torch.repeat_interleave(torch.arange(n_last - n_first, device=dev), deg)      # item index (0-based) per entry
+    c = col[f0:f1].to(torch.int64)
+    keep = (c >= u_lo) & (c < u_hi)
+    row_of, c = row_of[keep], (c[keep] - u_lo).to(torch.int32)
+    del keep
+    blk = torch.searchsorted(item_cuts[1:].contiguous(), row_of + n_first, right=True).clamp_(max=W - 1)
+    prow = blk * R_i + (row_of + n_first - item_cuts[blk])                                  # owner-block numbering
+    cnt = torch.bincount(prow, minlength=W * R_i)
+    rp_b = torch.zeros(W * R_i + 1, dtype=torch.int64, device=dev)
+    rp_b[1:] = torch.cumsum(cnt, 0)
+    # entries are already grouped by item in ascending item order and blocks ascend with the item id, so prow is sorted
+    return rp_a, col_a, rp_b.contiguous(), c.contiguous(), R_i, [int(x) for x in sizes.tolist()]
+
+
+class ReducePropagator:
+    """"reduce" partition for bipartite graphs with many more users than items (cfg-3: 10 M x 2 M).
+
+    The all-gather partition makes every rank ingest the WHOLE table per layer, and 5/6 of that is user rows
+    that only the item owners need.  Here user rows never travel: every rank sums its own users' pre-scaled
+    rows per item (graph B, raw fp32 partial sums pushed to the item's owner, `dst_route_rows`), the owner
+    adds the W partials and runs the usual row epilogue (`lgcn_reduce_rows`), and only the ITEM rows are
+    gathered (pushed from that epilogue, NVSwitch multicast when available).  Per layer and rank: item table in
+    + one item-table-sized partial out, instead of the whole table in.  Same buffers and padded ids as the push
+    partition: buf[b] holds the gathered items and, in its own block, this rank's users."""
+
+    def __init__(self, part: RowPartition, rank: int, rowptr, col, dinv_local: torch.Tensor, n_layers: int,
+                 ops, group, d: int, storage_dtype: torch.dtype, device, interleave: int = 32, use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm
+        from .graph import CsrGraph, decompose_rows
+        if part.side_split or len(part.cuts) != 2:
+            raise ValueError("the reduce partition needs the two-sided RowPartition")
+        self.part, self.rank, self.K, self.ops = part, rank, n_layers, ops
+        self.storage_dtype = storage_dtype
+        R, W = part.R, part.world
+        rp_a, col_a, rp_b, col_b, R_i, _ = reduce_local_graphs(part, rank, rowptr, col)
+        (u_lo, u_hi), (i_lo, i_hi) = part.ranges(rank)
+        self.nu, self.ni, self.R_i = u_hi - u_lo, i_hi - i_lo, R_i
+        self.dinv_u = dinv_local[:self.nu].contiguous()
+        self.dinv_i = dinv_local[self.nu:self.nu + self.ni].contiguous()
+        self.graph_a = CsrGraph(self.nu, 0, rp_a, col_a, self.dinv_u, **decompose_rows(rp_a))
+        self.ones = torch.ones(W * R_i, dtype=torch.float32, device=device)
+        self.graph_b = CsrGraph(W * R_i, 0, rp_b, col_b, self.ones, **decompose_rows(rp_b, interleave=interleave))
+        self.local_nnz = int(col_a.numel() + col_b.numel())
+        self.bufs = [symm.empty((W * R, d), dtype=storage_dtype, device=device).zero_() for _ in range(2)]
+        self.hdl = [symm.rendezvous(t, group) for t in self.bufs]
+        self.peers = [[int(h.buffer_ptrs[r]) for r in range(W)] for h in self.hdl]
+        self.mcast = [0, 0]
+        if use_multicast:
+            mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.hdl]
+            if all(mc):
+                self.mcast = mc
+        # partial sums at the owner: slot q = the partial of rank q for my item block
+        self.partials = symm.empty((W, R_i, d), dtype=torch.float32, device=device).zero_()
+        self.phdl = symm.rendezvous(self.partials, group)
+        self.ppeers = [int(self.phdl.buffer_ptrs[r]) for r in range(W)]
+        self.row0 = rank * R
+        self.x0_valid = False
+
+    def _barrier(self):
+        self.hdl[0].barrier(channel=0)
+
+    def _own(self, b: int) -> torch.Tensor:
+        """This rank's user rows inside gathered buffer b (they are read locally by graph B and never pushed)."""
+        return self.bufs[b][self.row0:self.row0 + self.nu]
+
+    def _item_push(self, b: int) -> dict:
+        t = dict(dst_multicast=self.mcast[b]) if self.mcast[b] else dict(dst_peers=self.peers[b])
+        return dict(dst=self.bufs[b], dst_row_offset=self.row0 + self.nu, **t)
+
+    def push_x0(self, emb_local: torch.Tensor) -> None:
+        ops = self.ops
+        self._barrier()  # every peer is done reading buf[0]
+        ops.scale_rows_push(emb_local[:self.nu], self.dinv_u, self.storage_dtype, [self.peers[0][self.rank]], self.row0)
+        ops.scale_rows_push(emb_local[self.nu:self.nu + self.ni], self.dinv_i, self.storage_dtype, self.peers[0],
+                            self.row0 + self.nu)
+        self.x0_valid = True
+
+    def _layer(self, src_buf, src_own, nxt, users_kw, items_kw, last_push: bool):
+        """One layer: user rows from the gathered items (A), item partials from the local users (B) pushed to
+        their owners, barrier, owner-side reduce + epilogue (item rows pushed to everyone when `nxt` is set)."""
+        ops = self.ops
+        ops.propagate_layer(self.graph_a, src_buf, scale_src=False,
+                            dst=None if nxt is None else self._own(nxt), **users_kw)
+        ops.propagate_layer(self.graph_b, src_own, scale_src=False, n_src_rows=self.nu, dst=self.partials[0],
+                            dst_peers=self.ppeers, dst_row_offset=self.rank * self.R_i, dst_route_rows=self.R_i,
+                            src_scale=self.ones, dst_scale=self.ones)
+        self.phdl.barrier(channel=2)          # every rank's partials for my items have landed
+        ops.reduce_rows(self.partials, self.ni, self.dinv_i, **({} if nxt is None else self._item_push(nxt)), **items_kw)
+
+    def forward(self, emb_local: torch.Tensor, acc: torch.Tensor, out: torch.Tensor) -> None:
+        K, nu, ni = self.K, self.nu, self.ni
+        if not self.x0_valid:
+            self.push_x0(emb_local)
+        for k in range(K):
+            last = k == K - 1
+            self._barrier()  # the item rows of layer k (or X0) are visible; everyone is done with the partials of layer k-1
+            b = k & 1
+            sc = 1.0 / (K + 1) if last else 1.0
+            ukw = dict(acc_in=emb_local[:nu] if k == 0 else acc[:nu], acc_out=(out if last else acc)[:nu], acc_scale=sc)
+            ikw = dict(acc_in=emb_local[nu:nu + ni] if k == 0 else acc[nu:nu + ni], acc_out=(out if last else acc)[nu:nu + ni],
+                       acc_scale=sc)
+            self._layer(self.bufs[b], self._own(b), None if last else (k + 1) & 1, ukw, ikw, not last)
+        if K > 1:
+            self.x0_valid = False
+
+    def backward(self, G_local: torch.Tensor, g0_src: torch.Tensor, **last_kwargs) -> None:
+        """Horner backward; layer j reads buf[(a + j) & 1] (j > 0) or the local seed g0, writes buf[(a + j + 1) & 1],
+        a = K & 1 so that the last layer's Adam epilogue leaves dinv (.) E_new in buf[0] (users locally, items pushed)."""
+        K, nu, ni = self.K, self.nu, self.ni
+        a = K & 1
+
+        def rows(kw, lo, hi):   # slice the per-row tensors of the Adam / gradient epilogue
+            out = dict(kw)
+            for key in ("cnt", "emb", "grad", "adam_m", "adam_v"):
+                if out.get(key) is not None:
+                    out[key] = out[key][lo:hi]
+            return out
+
+        for j in range(K):
+            last = j == K - 1
+            self._barrier()
+            nxt = (a + j + 1) & 1
+            src = g0_src if j == 0 else self.bufs[(a + j) & 1]
+            src_own = g0_src[self.row0:self.row0 + nu] if j == 0 else self._own((a + j) & 1)
+            kw = dict(last_kwargs, push_emb=True) if last else {}
+            self._layer(src, src_own, nxt, dict(base=G_local[:nu], **rows(kw, 0, nu)),
+                        dict(base=G_local[nu:nu + ni], **rows(kw, nu, nu + ni)), True)
+        self.x0_valid = True
+
+
 def exchange_rows(part: RowPartition, rank: int, local, padded_ids: torch.Tensor, group=None):
     """rows[i] = TABLE[padded_ids[i]] where TABLE is row-partitioned: owners fill, one all-reduce.
     `local` may be a list of tables (their rows are concatenated along dim 1 AFTER the gather, so
@@ -351,17 +504,23 @@ class DistLightGCN:
         # bipartite side split (users on the first W/2 ranks, items on the rest) halves the exchange
         # when the two sides have comparable row counts; cfg "dist_partition": "two_sided" keeps
         # every rank on both sides
-        mode_p = config.get("dist_partition", "auto")
+        mode_p = config.get("dist_partition", "auto")   # auto | side_split | two_sided | reduce
         if mode_p == "auto":   # cfg-3 (10 M users x 2 M items) keeps the measured two-sided cut: with one side
             # 5x larger the side split makes the item ranks ingest the whole user table anyway
             mode_p = "side_split" if max(self.n, self.m) <= 2 * min(self.n, self.m) else "two_sided"
         self.part = RowPartition(g.rowptr, world, n_users=self.n, side_split=(mode_p == "side_split"))
-        rp, colp, dl = self.part.local_csr(rank, g.rowptr, g.col, g.dinv)
-        # the push exchange stores every output row to the peers from the SpMM epilogue: interleave heavy and
-        # light row chunks so those stores are spread over the launch (graph.decompose_rows)
-        self.local_graph = CsrGraph(self.part.rows[rank], 0, rp, colp, dl,
-                                    **decompose_rows(rp, interleave=int(config.get("dist_row_interleave", 32))))
-        self.local_nnz = int(colp.numel())
+        self.reduce_mode = mode_p == "reduce"
+        if self.reduce_mode:
+            # "reduce": user rows never travel (ReducePropagator); only the local deg^-1/2 shard is needed here
+            dl = self.part.shard(rank, g.dinv)
+            self.local_graph, self.local_nnz = None, 0
+        else:
+            rp, colp, dl = self.part.local_csr(rank, g.rowptr, g.col, g.dinv)
+            # the push exchange stores every output row to the peers from the SpMM epilogue: interleave heavy and
+            # light row chunks so those stores are spread over the launch (graph.decompose_rows)
+            self.local_graph = CsrGraph(self.part.rows[rank], 0, rp, colp, dl,
+                                        **decompose_rows(rp, interleave=int(config.get("dist_row_interleave", 32))))
+            self.local_nnz = int(colp.numel())
         R, d, dev = self.part.R, self.d, self.device
         gen = torch.Generator(device=dev).manual_seed(seed + rank)
         self.emb = torch.randn((R, d), generator=gen, device=dev) * 0.1      # model/lgcn.py:75, local rows
@@ -380,7 +539,16 @@ class DistLightGCN:
         mode = config.get("dist_exchange", "auto")
         self.exchange = "nccl"
         self.prop = None
-        if world > 1 and mode in ("auto", "push"):
+        if self.reduce_mode:
+            if world < 2 or mode == "nccl":
+                raise ValueError("dist_partition='reduce' needs the push exchange on >= 2 ranks")
+            self.prop = ReducePropagator(self.part, rank, g.rowptr, g.col, dl, self.K, ops,
+                                         group if group is not None else dist.group.WORLD, d, storage, dev,
+                                         interleave=int(config.get("dist_row_interleave", 32)),
+                                         use_multicast=bool(config.get("dist_multicast", True)))
+            self.local_nnz = self.prop.local_nnz
+            self.exchange = "push"
+        elif world > 1 and mode in ("auto", "push"):
             try:
                 self.prop = PushPropagator(self.part, rank, self.local_graph, dl, self.K, ops,
                                            group if group is not None else dist.group.WORLD, d, storage, dev,

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LGCN_ABI_VERSION 3
+#define LGCN_ABI_VERSION 4
 
 #define LGCN_ERR_INVALID_ARG (-1)
 #define LGCN_ERR_UNSUPPORTED (-2)
@@ -153,10 +153,25 @@ typedef struct lgcn_layer_args {
    * gathered buffer of every rank of the mapping — instead of n_dst_peers unicast peer stores (the
    * per-rank NVLink egress drops from n_dst_peers rows to one).  dst must still be non-NULL. */
   void* dst_multicast;
+  /* > 0 (with dst_peers): every dst row has ONE destination — row i is stored to peer i / dst_route_rows only,
+   * at row dst_row_offset + i % dst_route_rows.  Used for the partial sums of the reduce partition
+   * (lgcn_reduce_rows): the rows of this launch are all items, in blocks of dst_route_rows per owner. */
+  int64_t dst_route_rows;
 } lgcn_layer_args_t;
 
 int lgcn_propagate_layer(const lgcn_graph_t* g /*HOST*/, const lgcn_layer_args_t* a /*HOST*/,
                          lgcn_stream_t stream);
+
+/* Owner-side half of the "reduce" partition (bipartite graphs with many more users than items): instead of
+ * all-gathering the user rows so that item owners can gather them, every rank sums ITS users' rows per item
+ * (lgcn_propagate_layer on the item x local-user CSR with unit scales and dst_route_rows: raw partial sums pushed
+ * to the item's owner) and the owner adds the n_parts partials and runs the usual row epilogue:
+ *   s_i = sum_q partials[q * part_rows + i]   (q ascending: deterministic),  i < n_rows
+ * then exactly lgcn_propagate_layer's epilogue with x_i = dst_scale_i * s_i (a->src is ignored; dinv is the
+ * owner's deg^-1/2 vector for these rows).  The per-layer exchange shrinks from the whole table to the item
+ * table plus one item-table-sized partial per rank. */
+int lgcn_reduce_rows(const float* partials, int n_parts, int64_t part_rows, int64_t n_rows, const float* dinv,
+                     const lgcn_layer_args_t* a /*HOST*/, lgcn_stream_t stream);
 
 /* dst_p[row_offset + i] = dinv[i] * x[i] on every peer p: the pre-scaled source of the first
  * layer, pushed straight into the peers' gathered buffers (no separate all-gather). */

@@ -165,3 +165,42 @@ def test_partitioned_propagation_world2_gloo(side_split):
             assert err_x == 0.0
             assert err_g0 < 1e-6, f"local layer-0 source differs from the exchanged one on rank {rank}: {err_g0}"
         assert ret[0][3] + ret[1][3] == 7 and ret[0][5] == ret[1][5]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_reduce_partition_graphs_reproduce_the_propagation(world):
+    """Index logic of the "reduce" partition (parallel.reduce_local_graphs), single process: user rows gathered
+    from the padded item table (graph A) plus, for every item, the sum over ranks of the partial sums over each
+    rank's local users (graph B, owner-block numbering) must equal A_hat X of the oracle."""
+    from furusato_recommend_b200.parallel import reduce_local_graphs
+    g = dict(np.load(GOLD))
+    n, m = int(g["n_users"]), int(g["m_items"])
+    csr = G.build_csr_graph(n, m, torch.from_numpy(g["train_user"]), torch.from_numpy(g["train_item"]))
+    part = RowPartition(csr.rowptr, world, n_users=n)
+    N, R = n + m, part.R
+    X = torch.from_numpy(g["E0"]).double()
+    graph = orc.sparse_graph(n, m, g["train_user"], g["train_item"]).to_dense().double()
+    want = graph @ X
+    Z = csr.dinv.double()[:, None] * X                                   # pre-scaled activations
+    padded = part.to_padded(torch.arange(N))
+    Zfull = torch.zeros(world * R, X.shape[1], dtype=torch.float64)
+    Zfull[padded] = Z
+    got = torch.zeros_like(want)
+    partial_sum = None
+    R_i = None
+    for r in range(world):
+        rp_a, col_a, rp_b, col_b, R_i, sizes = reduce_local_graphs(part, r, csr.rowptr, csr.col)
+        (u_lo, u_hi), _ = part.ranges(r)
+        rows_a = torch.repeat_interleave(torch.arange(u_hi - u_lo), rp_a[1:] - rp_a[:-1])
+        s = torch.zeros(u_hi - u_lo, X.shape[1], dtype=torch.float64).index_add_(0, rows_a, Zfull[col_a.long()])
+        got[u_lo:u_hi] = csr.dinv.double()[u_lo:u_hi, None] * s       # user rows: local gather from the item table
+        rows_b = torch.repeat_interleave(torch.arange(world * R_i), rp_b[1:] - rp_b[:-1])
+        p = torch.zeros(world * R_i, X.shape[1], dtype=torch.float64).index_add_(0, rows_b, Z[u_lo:u_hi][col_b.long()])
+        partial_sum = p if partial_sum is None else partial_sum + p       # what the owners' reduce kernel adds up
+        assert int(col_b.max()) < u_hi - u_lo and int(rp_b[-1]) == col_b.numel()
+    item_cuts = part.cuts[1]
+    for b in range(world):
+        lo, hi = int(item_cuts[b]), int(item_cuts[b + 1])
+        got[lo:hi] = csr.dinv.double()[lo:hi, None] * partial_sum[b * R_i:b * R_i + (hi - lo)]
+        assert float(partial_sum[b * R_i + (hi - lo):(b + 1) * R_i].abs().sum()) == 0.0   # padding rows stay empty
+    assert float((got - want).abs().max()) < 1e-6 * float(want.abs().max())

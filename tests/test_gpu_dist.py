@@ -71,11 +71,12 @@ def _gather(dm, local):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("exchange,partition", [("nccl", "two_sided"), ("push", "two_sided"), ("push", "side_split"),
-                                                ("nccl", "side_split")])
+                                                ("nccl", "side_split"), ("push", "reduce")])
 @pytest.mark.timeout(120)
 def test_row_partitioned_training_matches_reference_2gpu(exchange, partition):
     """nccl: ncclAllGather per layer; push: all-gather fused into the SpMM epilogue (NVLink peer stores) and
-    the whole step replayed as one CUDA graph.  side_split: users on rank 0, items on rank 1."""
+    the whole step replayed as one CUDA graph.  side_split: users on rank 0, items on rank 1.  reduce: user rows
+    never travel — per-item partial sums go to the item's owner (lgcn_reduce_rows), only item rows are gathered."""
     world, port = 2, _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
