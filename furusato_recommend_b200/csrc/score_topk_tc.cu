@@ -33,11 +33,6 @@
 
 #include <string>
 
-// Build with -DLGCN_TC_RS=1 to compile the experimental register-staged epilogue (layout "m2rs").
-#ifndef LGCN_TC_RS
-#define LGCN_TC_RS 0
-#endif
-
 #include "common.cuh"
 
 namespace lgcn {
@@ -45,6 +40,25 @@ namespace tc {
 
 constexpr int kUM = 128;      // users per CTA == UMMA M
 constexpr int kFrontWarps = 4;
+
+// -DLGCN_TC_PROF=1 (tuning builds only): CTA 0 accumulates clock64() deltas of the pipeline phases of one epilogue
+// warp and one MMA-issuing warp; lgcn_debug_tc_prof() reads them back.  [0..7] epilogue: wait-full, TMEM read,
+// max tree + vote, candidate path, hand-back, tiles, candidate entries, total; [8..12] issuer: wait B tile,
+// wait accumulator-empty, issue, tiles, total.
+#ifdef LGCN_TC_PROF
+__device__ long long g_tc_prof[24];   // [16..22]: candidate path split — masks, single take, multi path, compaction, #multi, #compactions
+// absolute clock64() stamps of CTA 0 for item tiles [kProfT0, kProfT0 + 8): issuer 0 {accumulator free, MMAs issued},
+// epilogue warp 0 {accumulator full, TMEM read done, handed back}
+__device__ long long g_tc_stamp[8][5];
+constexpr int kProfT0 = 6000;
+#define LGCN_STAMP(j, slot, cond) do { if ((cond) && (j) >= kProfT0 && (j) < kProfT0 + 8) g_tc_stamp[(j) - kProfT0][slot] = clock64(); } while (0)
+#define LGCN_PROF_T(var) const long long var = clock64()
+#define LGCN_PROF_ADD(slot, t0, t1) pf[slot] += (t1) - (t0)
+#else
+#define LGCN_PROF_T(var)
+#define LGCN_PROF_ADD(slot, t0, t1)
+#define LGCN_STAMP(j, slot, cond)
+#endif
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -346,20 +360,6 @@ __device__ __forceinline__ float max32_h(const uint32_t (&r)[32], float (&m4)[4]
   return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
 }
 
-// r[c] for a warp-uniform c: a dense switch (jump table), no dynamic register indexing
-__device__ __forceinline__ uint32_t pick32(const uint32_t (&r)[32], int c) {
-  uint32_t v = 0;
-  switch (c) {
-#define LGCN_PICK(i) case i: v = r[i]; break;
-    LGCN_PICK(0) LGCN_PICK(1) LGCN_PICK(2) LGCN_PICK(3) LGCN_PICK(4) LGCN_PICK(5) LGCN_PICK(6) LGCN_PICK(7)
-    LGCN_PICK(8) LGCN_PICK(9) LGCN_PICK(10) LGCN_PICK(11) LGCN_PICK(12) LGCN_PICK(13) LGCN_PICK(14) LGCN_PICK(15)
-    LGCN_PICK(16) LGCN_PICK(17) LGCN_PICK(18) LGCN_PICK(19) LGCN_PICK(20) LGCN_PICK(21) LGCN_PICK(22) LGCN_PICK(23)
-    LGCN_PICK(24) LGCN_PICK(25) LGCN_PICK(26) LGCN_PICK(27) LGCN_PICK(28) LGCN_PICK(29) LGCN_PICK(30) LGCN_PICK(31)
-#undef LGCN_PICK
-  }
-  return v;
-}
-
 struct Params {
   const uint4* a_packed;   // user tiles, [n_utiles][D/8][128]
   const uint4* b_packed;   // item tiles, [n_itiles][D/8][TN]
@@ -501,9 +501,19 @@ score_topk_tc_kernel(const Params p) {
     const uint64_t bdesc_base = make_desc(smem_u32(sB), TN * 16, 128);
     int s = 0, a = 0;
     uint32_t full_parity = 0, acc_round = 0;
+#ifdef LGCN_TC_PROF
+    long long pf[4] = {0, 0, 0, 0};
+    const long long pf_begin = clock64();
+#endif
     for (int j = 0; j < n_tiles; ++j) {
+      LGCN_PROF_T(q0);
       mbar_wait(bar_full + 8 * s, full_parity);
+      LGCN_PROF_T(q1);
       if (acc_round > 0) mbar_wait_hint(bar_tempty + 8 * (a * MT + mt), (acc_round - 1) & 1, p.wait_hint);
+      LGCN_PROF_T(q2);
+      LGCN_PROF_ADD(0, q0, q1);
+      LGCN_PROF_ADD(1, q1, q2);
+      LGCN_STAMP(j, 0, blockIdx.x == 0 && mt == 0 && lane == 0);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t bdesc0 = bdesc_base + (uint64_t)(((uint32_t)s * kBBytes) >> 4);
@@ -516,9 +526,18 @@ score_topk_tc_kernel(const Params p) {
         if constexpr (CL > 1) tc_commit_mc(bar_empty + 8 * s, kClusterMask); else tc_commit(bar_empty + 8 * s);
       }
       __syncwarp();
+      LGCN_PROF_T(q3);
+      LGCN_PROF_ADD(2, q2, q3);
+      LGCN_STAMP(j, 1, blockIdx.x == 0 && mt == 0 && lane == 0);
       if (++s == S) { s = 0; full_parity ^= 1u; }
       if (++a == NST) { a = 0; ++acc_round; }
     }
+#ifdef LGCN_TC_PROF
+    if (blockIdx.x == 0 && mt == 0 && lane == 0) {
+      g_tc_prof[8] = pf[0]; g_tc_prof[9] = pf[1]; g_tc_prof[10] = pf[2]; g_tc_prof[11] = n_tiles;
+      g_tc_prof[12] = clock64() - pf_begin;
+    }
+#endif
   } else if (warp >= kFrontWarps) {
     // ------------------------------------------------ epilogue: thread == user row
     const int ew = warp - kFrontWarps;
@@ -563,21 +582,46 @@ score_topk_tc_kernel(const Params p) {
     static_assert(CPG >= 1 && CPG * COLS * CG == TN, "every epilogue group needs whole chunks of the tile");
     const int c0 = cg * CPG;
 
-#if LGCN_TC_RS
     if constexpr (RS) {
+      // Register-staged epilogue ("m2rl"): the warp copies its 32 rows x 128 columns of the accumulator into
+      // registers and hands the TMEM stage back BEFORE any selection work, so a warp that runs into
+      // candidates no longer holds back its user tile's next MMA (with two TMEM stages the hand-off is
+      // otherwise coupled to the slowest of the four warps on every tile).  Candidates are handled
+      // lane-locally from the registers: a 16-bit mask of the 8-column blocks this lane hit, a dense
+      // switch that moves the hit block into 8 fixed registers, a predicated scan of those — no warp
+      // collectives and no TMEM re-reads on the candidate path.
+#ifdef LGCN_TC_PROF
+      long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const long long pf_begin = clock64();
+#endif
       for (int j = 0; j < n_tiles; ++j) {
         const int a = j % NST;
+        LGCN_PROF_T(q0);
         mbar_wait_hint(bar_tfull + 8 * (a * MT + mt), (j / NST) & 1, p.wait_hint);
+        LGCN_PROF_T(q1);
+        LGCN_PROF_ADD(0, q0, q1);
+        LGCN_STAMP(j, 2, blockIdx.x == 0 && ew == 0 && lane == 0);
         tc_fence_after();
         const uint32_t tbase = tmem_base + lane_base + (uint32_t)((a * MT + mt) * TN);
         uint32_t r[4][32];
         __syncwarp();
+        if (dbg != 1) {
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) tc_ld32(tbase + (uint32_t)(32 * q4), r[q4]);
-        tc_wait_ld();
+          for (int q4 = 0; q4 < 4; ++q4) tc_ld32(tbase + (uint32_t)(32 * q4), r[q4]);
+          tc_wait_ld();
+        }
         tc_fence_before();
         __syncwarp();
+        LGCN_STAMP(j, 3, blockIdx.x == 0 && ew == 0 && lane == 0);
         if (lane == 0) mbar_arrive(bar_tempty + 8 * (a * MT + mt));   // the accumulator lives in registers now
+        LGCN_STAMP(j, 4, blockIdx.x == 0 && ew == 0 && lane == 0);
+        LGCN_PROF_T(q2);
+        LGCN_PROF_ADD(1, q1, q2);
+        if (dbg == 1) continue;
+        if (dbg == 2) {   // pipeline experiment: TMEM reads only, no selection work
+          if ((r[0][0] ^ r[1][31] ^ r[2][0] ^ r[3][31]) == 0x7fc12345u) sel.cnt = 1;
+          continue;
+        }
         const int item_tile0 = j * TN;
         if (DUMP) {
           if (live) {
@@ -592,50 +636,83 @@ score_topk_tc_kernel(const Params p) {
         float m4[4][4], cm[4];
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) cm[q4] = max32(r[q4], m4[q4]);
-        if (__any_sync(0xffffffffu, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) > sel.thr)) {
+        const float cmax = fmaxf(fmax3(cm[0], cm[1], cm[2]), cm[3]);
+        const bool slow_entry = __any_sync(0xffffffffu, cmax > sel.thr);
+        LGCN_PROF_T(q3);
+        LGCN_PROF_ADD(2, q2, q3);
+        if (slow_entry) {
+          if (cmax > sel.thr) {
+            uint32_t bm = 0;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            if (!__any_sync(0xffffffffu, cm[q4] > sel.thr)) continue;
-            uint32_t hm = 0;
+            for (int q4 = 0; q4 < 4; ++q4)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              if (__any_sync(0xffffffffu, m4[q4][b] > sel.thr)) {
+              for (int b = 0; b < 4; ++b) bm |= (m4[q4][b] > sel.thr) ? (1u << (4 * q4 + b)) : 0u;
+            while (bm) {   // hit blocks in ascending column order
+              const int blk = __ffs(bm) - 1;
+              bm &= bm - 1;
+              uint32_t v[8];
 #pragma unroll
-                for (int i = 8 * b; i < 8 * b + 8; ++i) hm |= (__uint_as_float(r[q4][i]) > sel.thr) ? (1u << i) : 0u;
+              for (int i = 0; i < 8; ++i) v[i] = 0xff800000u;   // -inf
+              switch (blk) {
+#define LGCN_BLK(n)                                                             \
+  case n:                                                                       \
+    _Pragma("unroll") for (int i = 0; i < 8; ++i) v[i] = r[(n) >> 2][8 * ((n) & 3) + i]; \
+    break;
+                LGCN_BLK(0) LGCN_BLK(1) LGCN_BLK(2) LGCN_BLK(3) LGCN_BLK(4) LGCN_BLK(5) LGCN_BLK(6) LGCN_BLK(7)
+                LGCN_BLK(8) LGCN_BLK(9) LGCN_BLK(10) LGCN_BLK(11) LGCN_BLK(12) LGCN_BLK(13) LGCN_BLK(14) LGCN_BLK(15)
+#undef LGCN_BLK
               }
-            }
-            uint32_t any = __reduce_or_sync(0xffffffffu, hm);
-            while (any) {
-              const int c = __ffs(any) - 1;
-              any &= any - 1;
-              __syncwarp();
-              const uint32_t raw = pick32(r[q4], c);
-              if ((hm >> c) & 1u) {
-                const int item = item_tile0 + 32 * q4 + c;
-                while (next_pos < item) {   // walk of the sorted train positives (ascending sweep)
-                  ++pp;
-                  next_pos = pp < my_npos ? __ldg(my_pos + pp) : 0x7fffffff;
-                }
-                const float v = next_pos == item ? p.mask_value : __uint_as_float(raw);  // trainer.py:137
-                if (item < p.m_items && v > sel.thr) {
-                  if (sel.cnt == p.cap) sel = sel_compact(sel, mv, mi, NT, p.k);
-                  if (v > sel.thr) {
-                    mv[sel.cnt * NT] = v;
-                    mi[sel.cnt * NT] = item;
-                    ++sel.cnt;
+              const int ib = item_tile0 + 8 * blk;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float raw = __uint_as_float(v[i]);
+                if (raw > sel.thr) {
+                  const int item = ib + i;
+                  while (next_pos < item) {   // walk of the sorted train positives (ascending sweep)
+                    ++pp;
+                    next_pos = pp < my_npos ? __ldg(my_pos + pp) : 0x7fffffff;
+                  }
+                  const float vv = next_pos == item ? p.mask_value : raw;  // trainer.py:137
+                  if (item < p.m_items && vv > sel.thr) {   // item >= m_items: zero padding of the last tile
+                    if (sel.cnt == p.cap) sel = sel_compact(sel, mv, mi, NT, p.k);  // rare: threshold still -inf
+                    if (vv > sel.thr) {
+                      mv[sel.cnt * NT] = vv;
+                      mi[sel.cnt * NT] = item;
+                      ++sel.cnt;
+                    }
                   }
                 }
               }
             }
           }
+          __syncwarp();
           if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
+          LGCN_PROF_T(q4);
+          LGCN_PROF_ADD(3, q3, q4);
+#ifdef LGCN_TC_PROF
+          pf[6] += 1;
+#endif
         }
       }
-    } else
+#ifdef LGCN_TC_PROF
+      if (blockIdx.x == 0 && ew == 0 && lane == 0) {
+        for (int i = 0; i < 5; ++i) g_tc_prof[i] = pf[i];
+        g_tc_prof[5] = n_tiles; g_tc_prof[6] = pf[6]; g_tc_prof[7] = clock64() - pf_begin;
+      }
+#endif
+    } else {
+#ifdef LGCN_TC_PROF
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long ps[6] = {0, 0, 0, 0, 0, 0};
+    const long long pf_begin = clock64();
 #endif
     for (int j = 0; j < n_tiles; ++j) {
       const int a = j % NST;
+      LGCN_PROF_T(q0);
       mbar_wait_hint(bar_tfull + 8 * (a * MT + mt), (j / NST) & 1, p.wait_hint);
+      LGCN_PROF_T(q1);
+      LGCN_PROF_ADD(0, q0, q1);
+      LGCN_STAMP(j, 2, blockIdx.x == 0 && ew == 0 && lane == 0);
       tc_fence_after();
       const int item_tile0 = j * TN + c0 * COLS;
       const uint32_t tbase = tmem_base + lane_base + (uint32_t)((a * MT + mt) * TN + c0 * COLS);
@@ -643,6 +720,7 @@ score_topk_tc_kernel(const Params p) {
       for (int cc = 0; cc < CPG * n_chunks_dbg; ++cc) {
         uint32_t r[32], r2[32];
         __syncwarp();
+        LGCN_PROF_T(c0t);
         if (ACC16) {
           tc_ld32_pack16(tbase + (uint32_t)(cc * COLS), r);
         } else {
@@ -650,6 +728,9 @@ score_topk_tc_kernel(const Params p) {
           tc_ld32(tbase + (uint32_t)(cc * COLS + 32), r2);
         }
         tc_wait_ld();
+        LGCN_PROF_T(c1t);
+        LGCN_PROF_ADD(1, c0t, c1t);
+        LGCN_STAMP(j, 3, blockIdx.x == 0 && ew == 0 && lane == 0);
         if (dbg == 2) {   // pipeline experiment: TMEM reads only, no selection work
           if ((r[0] ^ r[31] ^ (ACC16 ? 0u : r2[0] ^ r2[31])) == 0x7fc12345u) sel.cnt = 1;
           continue;
@@ -679,54 +760,99 @@ score_topk_tc_kernel(const Params p) {
           float m4a[4], m4b[4];
           const float cma = max32(r, m4a);
           const float cmb = max32(r2, m4b);
-          if (__any_sync(0xffffffffu, fmaxf(cma, cmb) > sel.thr)) {
+          const float cm = fmaxf(cma, cmb);
+          const bool slow_entry = __any_sync(0xffffffffu, cm > sel.thr);
+          LGCN_PROF_T(c2t);
+          LGCN_PROF_ADD(2, c1t, c2t);
+          if (slow_entry) {
             // one candidate of this lane: positives walk, mask, append (ascending item ids)
-            auto take = [&](uint32_t hm, int c, int item, uint32_t raw) {
-              if ((hm >> c) & 1u) {
-                while (next_pos < item) {   // walk of the sorted train positives (ascending sweep)
-                  ++pp;
-                  next_pos = pp < my_npos ? __ldg(my_pos + pp) : 0x7fffffff;
-                }
-                const float v = next_pos == item ? p.mask_value : __uint_as_float(raw);  // trainer.py:137
-                if (item < p.m_items && v > sel.thr) {   // item >= m_items: zero padding of the last tile
-                  if (sel.cnt == p.cap) sel = sel_compact(sel, mv, mi, NT, p.k);  // rare: threshold still -inf
-                  if (v > sel.thr) {
-                    mv[sel.cnt * NT] = v;
-                    mi[sel.cnt * NT] = item;
-                    ++sel.cnt;
-                  }
+            auto take = [&](int item, uint32_t raw) {
+              while (next_pos < item) {   // walk of the sorted train positives (ascending sweep)
+                ++pp;
+                next_pos = pp < my_npos ? __ldg(my_pos + pp) : 0x7fffffff;
+              }
+              const float v = next_pos == item ? p.mask_value : __uint_as_float(raw);  // trainer.py:137
+              if (item < p.m_items && v > sel.thr) {   // item >= m_items: zero padding of the last tile
+                if (sel.cnt == p.cap) sel = sel_compact(sel, mv, mi, NT, p.k);  // rare: threshold still -inf
+                if (v > sel.thr) {
+                  mv[sel.cnt * NT] = v;
+                  mi[sel.cnt * NT] = item;
+                  ++sel.cnt;
                 }
               }
             };
-            auto slow_half = [&](const uint32_t(&rr)[32], const float(&m4)[4], float cm, int item_base, uint32_t tcol) {
-              if (!__any_sync(0xffffffffu, cm > sel.thr)) return;
-              // per-lane hit mask, built only for the 8-column blocks some lane of the warp hit
-              uint32_t hm = 0;
+            // Every slow-path instruction of ONE warp is on the critical path of its user tile (two TMEM stages:
+            // the four warps of a tile hand the accumulator back together), at ~5 clocks per dependent
+            // instruction — so the common case is kept lane-local and short.  Per-lane hit masks, built only
+            // for the 8-column blocks THIS lane hit (no block votes); a lane with exactly one hit already holds
+            // its value — it is the chunk maximum — and takes it without re-reading anything.
+            uint32_t hma = 0, hmb = 0;
+            if (cm > sel.thr) {
 #pragma unroll
               for (int b = 0; b < 4; ++b) {
-                if (__any_sync(0xffffffffu, m4[b] > sel.thr)) {
+                if (m4a[b] > sel.thr) {
 #pragma unroll
-                  for (int i = 8 * b; i < 8 * b + 8; ++i) hm |= (__uint_as_float(rr[i]) > sel.thr) ? (1u << i) : 0u;
+                  for (int i = 8 * b; i < 8 * b + 8; ++i) hma |= (__uint_as_float(r[i]) > sel.thr) ? (1u << i) : 0u;
+                }
+                if (m4b[b] > sel.thr) {
+#pragma unroll
+                  for (int i = 8 * b; i < 8 * b + 8; ++i) hmb |= (__uint_as_float(r2[i]) > sel.thr) ? (1u << i) : 0u;
                 }
               }
-              uint32_t any = __reduce_or_sync(0xffffffffu, hm);
-              while (any) {   // two columns per round: both re-reads are in flight before the one wait
-                const int ca = __ffs(any) - 1;
-                any &= any - 1;
-                const bool two = any != 0;
-                const int cb = two ? __ffs(any) - 1 : ca;
-                any &= any - 1;   // no-op when any == 0
-                __syncwarp();     // the candidate handling below diverges; tcgen05.ld is warp-collective
-                const uint32_t ra = tc_ld1(tcol + (uint32_t)ca);
-                const uint32_t rb = tc_ld1(tcol + (uint32_t)cb);
-                tc_wait_ld();
-                take(hm, ca, item_base + ca, ra);
-                if (two) take(hm, cb, item_base + cb, rb);
-              }
-            };
-            slow_half(r, m4a, cma, item0, tbase + (uint32_t)(cc * COLS));
-            slow_half(r2, m4b, cmb, item0 + 32, tbase + (uint32_t)(cc * COLS + 32));
+            }
+            const int nh = __popc(hma) + __popc(hmb);
+#ifdef LGCN_TC_PROF
+            __syncwarp();
+            const long long s1 = clock64();
+            ps[0] += s1 - c2t;
+#endif
+            if (nh == 1) take(item0 + (hma ? __ffs(hma) - 1 : 31 + __ffs(hmb)), __float_as_uint(cm));
+#ifdef LGCN_TC_PROF
+            __syncwarp();
+            const long long s2 = clock64();
+            ps[1] += s2 - s1;
+#endif
+            // several hits in one lane (the first tiles of a sweep, then rare): walk the columns those lanes hit
+            // in ascending order, RE-READING each column from TMEM (1-register tcgen05.ld with a warp-uniform
+            // column; the accumulator stage is still ours) instead of indexing live registers
+            if (__any_sync(0xffffffffu, nh > 1)) {
+              auto multi_half = [&](uint32_t hm, int item_base, uint32_t tcol) {
+                uint32_t any = __reduce_or_sync(0xffffffffu, hm);
+                while (any) {   // two columns per round: both re-reads are in flight before the one wait
+                  const int ca = __ffs(any) - 1;
+                  any &= any - 1;
+                  const bool two = any != 0;
+                  const int cb = two ? __ffs(any) - 1 : ca;
+                  any &= any - 1;   // no-op when any == 0
+                  __syncwarp();     // the candidate handling below diverges; tcgen05.ld is warp-collective
+                  const uint32_t ra = tc_ld1(tcol + (uint32_t)ca);
+                  const uint32_t rb = tc_ld1(tcol + (uint32_t)cb);
+                  tc_wait_ld();
+                  if ((hm >> ca) & 1u) take(item_base + ca, ra);
+                  if (two && ((hm >> cb) & 1u)) take(item_base + cb, rb);
+                }
+              };
+              const bool multi = nh > 1;
+              multi_half(multi ? hma : 0u, item0, tbase + (uint32_t)(cc * COLS));
+              multi_half(multi ? hmb : 0u, item0 + 32, tbase + (uint32_t)(cc * COLS + 32));
+#ifdef LGCN_TC_PROF
+              ps[4] += 1;
+#endif
+            }
+#ifdef LGCN_TC_PROF
+            const long long s3 = clock64();
+            ps[2] += s3 - s2;
+            const bool do_compact = __any_sync(0xffffffffu, sel.cnt >= trig);
+            if (do_compact) { sel = sel_compact(sel, mv, mi, NT, p.k); ps[5] += 1; }
+            ps[3] += clock64() - s3;
+#else
             if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
+#endif
+            LGCN_PROF_T(c3t);
+            LGCN_PROF_ADD(3, c2t, c3t);
+#ifdef LGCN_TC_PROF
+            pf[6] += 1;
+#endif
           }
         } else {
           float m4[4];
@@ -755,9 +881,21 @@ score_topk_tc_kernel(const Params p) {
         }
       }
       // one arrival per warp (128 same-address mbarrier arrives per hand-off serialise in shared memory)
+      LGCN_PROF_T(q4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * (a * MT + mt));
+      LGCN_PROF_T(q5);
+      LGCN_PROF_ADD(4, q4, q5);
+      LGCN_STAMP(j, 4, blockIdx.x == 0 && ew == 0 && lane == 0);
+    }
+#ifdef LGCN_TC_PROF
+    if (blockIdx.x == 0 && ew == 0 && lane == 0) {
+      for (int i = 0; i < 5; ++i) g_tc_prof[i] = pf[i];
+      g_tc_prof[5] = n_tiles; g_tc_prof[6] = pf[6]; g_tc_prof[7] = clock64() - pf_begin;
+      for (int i = 0; i < 6; ++i) g_tc_prof[16 + i] = ps[i];
+    }
+#endif
     }
 
     sel = sel_compact(sel, mv, mi, NT, p.k);
@@ -961,9 +1099,7 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
   const std::string& layout = tuning().layout;
   if constexpr (D <= 64) {
     if (k <= 24 && !acc16) {
-#if LGCN_TC_RS
-      if (layout == "m2rs") return run_cfg<D, 128, 2, 2, 2, true>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
-#endif
+      if (layout == "m2rl") return run_cfg<D, 128, 2, 2, 2, true>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
       if (layout == "m2s4") return run_cfg<D, 64, 2, 2, 4>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);   // 4 TMEM stages x 64 columns
       if (layout == "m2c2") return run_cfg<D, 128, 2, 2, 2, false, 2>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
       if (layout == "m2c4") return run_cfg<D, 128, 2, 2, 2, false, 4>(LGCN_TC_ARGS, 48, LGCN_TC_TAIL);
@@ -989,6 +1125,15 @@ static int run(const float* user_emb, const float* item_emb, const int64_t* user
 #undef LGCN_TC_TAIL
 
 }  // namespace tc
+
+#ifdef LGCN_TC_PROF
+extern "C" int lgcn_debug_tc_prof(long long* out16) {
+  return (int)cudaMemcpyFromSymbol(out16, tc::g_tc_prof, sizeof(long long) * 24);
+}
+extern "C" int lgcn_debug_tc_stamps(long long* out40) {
+  return (int)cudaMemcpyFromSymbol(out40, tc::g_tc_stamp, sizeof(long long) * 40);
+}
+#endif
 
 size_t score_topk_tc_workspace(int64_t n_eval, int64_t m_items, int d) {
   // covers every layout: user tiles rounded up to whole clusters (MT = 2 x CL = 4), item tiles at the widest TN
