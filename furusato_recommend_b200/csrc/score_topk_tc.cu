@@ -254,34 +254,93 @@ pack_bf16_kernel(const float* __restrict__ src, const int64_t* __restrict__ ids,
 
 // ---------------------------------------------------------------- selection
 struct Sel {
-  float thr;   // current k-th best value of this thread's list (-inf until k entries exist)
-  int cnt;     // entries in the buffer
-  int sorted;  // entries [0, sorted) are ordered by (value desc, id asc)
+  float thr;   // admission threshold: the smallest value of the held top-k set (-inf until k entries exist)
+  int cnt;     // entries in the buffer: [0, have) is the set, [have, cnt) were appended since the last fold
+  int have;    // size of the set (<= k); the set is NOT kept sorted (sel_finalize orders it once, at the end)
+  int mp;      // slot of the set's worst entry when have == k
 };
 
-// Fold the unsorted tail [sorted, cnt) into the sorted top-k prefix.  New entries carry
-// larger ids than everything already held, so on equal value they go AFTER (strict <).
+// Worst entry of the set [0, k): the smallest value; among equal values the largest id (it arrived last, and
+// the final order is (value desc, id asc)).
+__device__ __forceinline__ void sel_scan_min(const float* cval, const int* cidx, int NT, int k, float& minv,
+                                             int& minpos) {
+  // two passes over the values, 8 independent shared-memory loads at a time (a one-entry-at-a-time scan is a
+  // chain of k load latencies: 1200 clocks at k = 20); ids are only read for the entries that tie the minimum
+  float mv = INFINITY;
+  for (int q0 = 0; q0 < k; q0 += 8) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = q0 + i < k ? cval[(q0 + i) * NT] : INFINITY;
+    mv = fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(fminf(x[4], x[5]), fminf(fminf(x[6], x[7]), mv)));
+  }
+  int mid = -1, mpos = 0;
+  for (int q0 = 0; q0 < k; q0 += 8) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = q0 + i < k ? cval[(q0 + i) * NT] : INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (x[i] == mv) {
+        const int xi = cidx[(q0 + i) * NT];
+        if (xi > mid) {
+          mid = xi;
+          mpos = q0 + i;
+        }
+      }
+    }
+  }
+  minv = mv;
+  minpos = mpos;
+}
+
+// Fold the appended entries [have, cnt) into the top-k set.  The set is unordered: an admitted entry replaces
+// the worst one and the worst is found again by one scan of k independent loads — the sorted insertion this
+// replaces cost ~14 000 clocks per call (k dependent shared-memory round trips per inserted entry, measured
+// with the LGCN_TC_PROF build).  Appended entries carry larger ids than everything already held, so on an
+// equal value the newcomer loses (strict >).
 __device__ __noinline__ Sel sel_compact(Sel s, float* cval, int* cidx, int NT, int k) {
-  for (int e = s.sorted; e < s.cnt; ++e) {
+  int e = s.have;
+  if (s.have < k) {   // fill phase: the appended entries sit right behind the set
+    s.have = s.cnt < k ? s.cnt : k;
+    e = s.have;
+    if (s.have < k) {
+      s.cnt = s.have;
+      s.thr = -INFINITY;
+      return s;
+    }
+    sel_scan_min(cval, cidx, NT, k, s.thr, s.mp);
+  }
+  for (; e < s.cnt; ++e) {
+    const float v = cval[e * NT];
+    if (v > s.thr) {
+      cval[s.mp * NT] = v;
+      cidx[s.mp * NT] = cidx[e * NT];
+      sel_scan_min(cval, cidx, NT, k, s.thr, s.mp);
+    }
+  }
+  s.cnt = k;
+  return s;
+}
+
+// End of the sweep: fold, then order the set by (value desc, id asc) — once per row.
+__device__ __noinline__ Sel sel_finalize(Sel s, float* cval, int* cidx, int NT, int k) {
+  s = sel_compact(s, cval, cidx, NT, k);
+  for (int e = 1; e < s.have; ++e) {
     const float v = cval[e * NT];
     const int id = cidx[e * NT];
-    int p;
-    if (s.sorted < k) {
-      p = s.sorted++;
-    } else {
-      if (!(v > cval[(k - 1) * NT])) continue;
-      p = k - 1;
-    }
-    while (p > 0 && cval[(p - 1) * NT] < v) {
-      cval[p * NT] = cval[(p - 1) * NT];
-      cidx[p * NT] = cidx[(p - 1) * NT];
+    int p = e;
+    while (p > 0) {
+      const float u = cval[(p - 1) * NT];
+      const int ui = cidx[(p - 1) * NT];
+      if (u > v || (u == v && ui < id)) break;
+      cval[p * NT] = u;
+      cidx[p * NT] = ui;
       --p;
     }
     cval[p * NT] = v;
     cidx[p * NT] = id;
   }
-  s.cnt = s.sorted;
-  s.thr = s.sorted == k ? cval[(k - 1) * NT] : -INFINITY;
+  s.cnt = s.have;
   return s;
 }
 
@@ -339,6 +398,52 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32], float (&m4)[4]) 
     m4[b] = fmax3(x, y, fmaxf(__uint_as_float(r[8 * b + 6]), __uint_as_float(r[8 * b + 7])));
   }
   return fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+}
+
+// ---- argmax of a 64-column chunk by descent through the maxima the fast path already holds.
+// A lane that hit in a chunk almost always has exactly ONE candidate, and that candidate is the chunk maximum
+// `cm`; only its column is unknown.  Static code walks the halves whose maximum equals cm (left first, so the
+// lowest column wins a tie) — 6 compare+branch steps and ~8 max instructions on the path — and collects the
+// maxima of the halves it did NOT enter: their maximum is the second largest value of the chunk, which tells
+// whether the lane has more than one candidate (then the general path runs).
+template <int I>
+__device__ __forceinline__ float colv(const uint32_t (&r)[32], const uint32_t (&r2)[32]) {
+  if constexpr (I < 32) return __uint_as_float(r[I]); else return __uint_as_float(r2[I - 32]);
+}
+template <int LO, int N>
+__device__ __forceinline__ float rangemax(const uint32_t (&r)[32], const uint32_t (&r2)[32], const float (&m4a)[4],
+                                          const float (&m4b)[4], float cma, float cmb) {
+  if constexpr (N == 32) {
+    return LO == 0 ? cma : cmb;
+  } else if constexpr (N == 16) {
+    if constexpr (LO < 32) return fmaxf(m4a[LO / 8], m4a[LO / 8 + 1]); else return fmaxf(m4b[(LO - 32) / 8], m4b[(LO - 32) / 8 + 1]);
+  } else if constexpr (N == 8) {
+    if constexpr (LO < 32) return m4a[LO / 8]; else return m4b[(LO - 32) / 8];
+  } else if constexpr (N == 4) {
+    return fmaxf(fmax3(colv<LO>(r, r2), colv<LO + 1>(r, r2), colv<LO + 2>(r, r2)), colv<LO + 3>(r, r2));
+  } else if constexpr (N == 2) {
+    return fmaxf(colv<LO>(r, r2), colv<LO + 1>(r, r2));
+  } else {
+    return colv<LO>(r, r2);
+  }
+}
+template <int LO, int N>
+__device__ __forceinline__ void descend(const uint32_t (&r)[32], const uint32_t (&r2)[32], const float (&m4a)[4],
+                                        const float (&m4b)[4], float cma, float cmb, float cm, float& second,
+                                        int& col) {
+  if constexpr (N == 1) {
+    col = LO;
+  } else {
+    const float ml = rangemax<LO, N / 2>(r, r2, m4a, m4b, cma, cmb);
+    const float mr = rangemax<LO + N / 2, N / 2>(r, r2, m4a, m4b, cma, cmb);
+    if (ml == cm) {
+      second = fmaxf(second, mr);
+      descend<LO, N / 2>(r, r2, m4a, m4b, cma, cmb, cm, second, col);
+    } else {
+      second = fmaxf(second, ml);
+      descend<LO + N / 2, N / 2>(r, r2, m4a, m4b, cma, cmb, cm, second, col);
+    }
+  }
 }
 
 __device__ __forceinline__ __half2 as_h2(uint32_t x) { return *reinterpret_cast<__half2*>(&x); }
@@ -563,7 +668,8 @@ score_topk_tc_kernel(const Params p) {
     const int n_chunks_dbg = dbg == 1 ? 0 : 1;
     sel.thr = (live && dbg < 3) ? -INFINITY : INFINITY;   // debug 3: max tree only, no candidate ever passes
     sel.cnt = 0;
-    sel.sorted = 0;
+    sel.have = 0;
+    sel.mp = 0;
     // warp-synchronous compaction once any lane holds k + 6 entries (at most cap - 4): folding early
     // keeps the thresholds tight, and every candidate that is not admitted saves a slow-path trip
     // for the whole warp (trigger 22 / 26 / 30 / 36 / 44 at k = 20: 626 / 663 / 657 / 645 / 632 TFLOP/s)
@@ -572,6 +678,10 @@ score_topk_tc_kernel(const Params p) {
     // walk of the user's sorted train positives, in step with the item sweep
     int pp = 0;
     int next_pos = my_npos > 0 ? __ldg(my_pos) : 0x7fffffff;
+    // the positive after next_pos, loaded one step ahead: an advance of the walk is a register move, the
+    // global load it issues is only needed by the advance after it (its ~500 clocks sat on every candidate
+    // that stepped over a positive)
+    int ahead_pos = my_npos > 1 ? __ldg(my_pos + 1) : 0x7fffffff;
     // the column groups of a user tile split every item tile; group cg owns chunks [cg*CPG, (cg+1)*CPG).
     // A chunk is 64 columns: two tcgen05.ld.x32 in flight (fp32), or one packed-f16 load (ACC16).
     // Two independent max trees per trip halve the exposed latency chain (TMEM load -> tree ->
@@ -670,7 +780,8 @@ score_topk_tc_kernel(const Params p) {
                   const int item = ib + i;
                   while (next_pos < item) {   // walk of the sorted train positives (ascending sweep)
                     ++pp;
-                    next_pos = pp < my_npos ? __ldg(my_pos + pp) : 0x7fffffff;
+                    next_pos = ahead_pos;
+                    ahead_pos = pp + 1 < my_npos ? __ldg(my_pos + pp + 1) : 0x7fffffff;
                   }
                   const float vv = next_pos == item ? p.mask_value : raw;  // trainer.py:137
                   if (item < p.m_items && vv > sel.thr) {   // item >= m_items: zero padding of the last tile
@@ -731,10 +842,12 @@ score_topk_tc_kernel(const Params p) {
         LGCN_PROF_T(c1t);
         LGCN_PROF_ADD(1, c0t, c1t);
         LGCN_STAMP(j, 3, blockIdx.x == 0 && ew == 0 && lane == 0);
+#ifdef LGCN_TC_PROF   // tuning builds only: the test does not belong in the per-chunk loop of the product
         if (dbg == 2) {   // pipeline experiment: TMEM reads only, no selection work
           if ((r[0] ^ r[31] ^ (ACC16 ? 0u : r2[0] ^ r2[31])) == 0x7fc12345u) sel.cnt = 1;
           continue;
         }
+#endif
         const int item0 = item_tile0 + cc * COLS;
         if (DUMP) {
           if (live) {
@@ -769,7 +882,8 @@ score_topk_tc_kernel(const Params p) {
             auto take = [&](int item, uint32_t raw) {
               while (next_pos < item) {   // walk of the sorted train positives (ascending sweep)
                 ++pp;
-                next_pos = pp < my_npos ? __ldg(my_pos + pp) : 0x7fffffff;
+                next_pos = ahead_pos;
+                ahead_pos = pp + 1 < my_npos ? __ldg(my_pos + pp + 1) : 0x7fffffff;
               }
               const float v = next_pos == item ? p.mask_value : __uint_as_float(raw);  // trainer.py:137
               if (item < p.m_items && v > sel.thr) {   // item >= m_items: zero padding of the last tile
@@ -782,40 +896,43 @@ score_topk_tc_kernel(const Params p) {
               }
             };
             // Every slow-path instruction of ONE warp is on the critical path of its user tile (two TMEM stages:
-            // the four warps of a tile hand the accumulator back together), at ~5 clocks per dependent
-            // instruction — so the common case is kept lane-local and short.  Per-lane hit masks, built only
-            // for the 8-column blocks THIS lane hit (no block votes); a lane with exactly one hit already holds
-            // its value — it is the chunk maximum — and takes it without re-reading anything.
-            uint32_t hma = 0, hmb = 0;
-            if (cm > sel.thr) {
-#pragma unroll
-              for (int b = 0; b < 4; ++b) {
-                if (m4a[b] > sel.thr) {
-#pragma unroll
-                  for (int i = 8 * b; i < 8 * b + 8; ++i) hma |= (__uint_as_float(r[i]) > sel.thr) ? (1u << i) : 0u;
-                }
-                if (m4b[b] > sel.thr) {
-#pragma unroll
-                  for (int i = 8 * b; i < 8 * b + 8; ++i) hmb |= (__uint_as_float(r2[i]) > sel.thr) ? (1u << i) : 0u;
-                }
-              }
-            }
-            const int nh = __popc(hma) + __popc(hmb);
+            // the four warps of a tile hand the accumulator back together) and runs at 6-15 clocks per
+            // instruction (cold, branchy, one warp) — measured 1600 clocks per entry before this version, 500 of
+            // them in per-lane hit masks.  The common case is lane-local and short: a lane with a candidate finds
+            // the column of its chunk maximum by descent (above); if the second largest value of the chunk is
+            // below the threshold that maximum is the lane's only candidate and is taken as is.
+            const bool mine = cm > sel.thr;
+            int col = 0;
+            float second = -INFINITY;
+            if (mine) descend<0, 64>(r, r2, m4a, m4b, cma, cmb, cm, second, col);
+            const bool multi = mine && second > sel.thr;
+            if (mine && !multi) take(item0 + col, __float_as_uint(cm));
 #ifdef LGCN_TC_PROF
             __syncwarp();
             const long long s1 = clock64();
             ps[0] += s1 - c2t;
-#endif
-            if (nh == 1) take(item0 + (hma ? __ffs(hma) - 1 : 31 + __ffs(hmb)), __float_as_uint(cm));
-#ifdef LGCN_TC_PROF
-            __syncwarp();
-            const long long s2 = clock64();
-            ps[1] += s2 - s1;
+            const long long s2 = s1;
 #endif
             // several hits in one lane (the first tiles of a sweep, then rare): walk the columns those lanes hit
             // in ascending order, RE-READING each column from TMEM (1-register tcgen05.ld with a warp-uniform
             // column; the accumulator stage is still ours) instead of indexing live registers
-            if (__any_sync(0xffffffffu, nh > 1)) {
+            if (__any_sync(0xffffffffu, multi || sel.cnt >= trig)) {   // one vote guards both rare paths
+            if (__any_sync(0xffffffffu, multi)) {
+              // per-lane hit masks of the lanes with several candidates, built only for the 8-column blocks they hit
+              uint32_t hma = 0, hmb = 0;
+              if (multi) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                  if (m4a[b] > sel.thr) {
+#pragma unroll
+                    for (int i = 8 * b; i < 8 * b + 8; ++i) hma |= (__uint_as_float(r[i]) > sel.thr) ? (1u << i) : 0u;
+                  }
+                  if (m4b[b] > sel.thr) {
+#pragma unroll
+                    for (int i = 8 * b; i < 8 * b + 8; ++i) hmb |= (__uint_as_float(r2[i]) > sel.thr) ? (1u << i) : 0u;
+                  }
+                }
+              }
               auto multi_half = [&](uint32_t hm, int item_base, uint32_t tcol) {
                 uint32_t any = __reduce_or_sync(0xffffffffu, hm);
                 while (any) {   // two columns per round: both re-reads are in flight before the one wait
@@ -832,9 +949,8 @@ score_topk_tc_kernel(const Params p) {
                   if (two && ((hm >> cb) & 1u)) take(item_base + cb, rb);
                 }
               };
-              const bool multi = nh > 1;
-              multi_half(multi ? hma : 0u, item0, tbase + (uint32_t)(cc * COLS));
-              multi_half(multi ? hmb : 0u, item0 + 32, tbase + (uint32_t)(cc * COLS + 32));
+              multi_half(hma, item0, tbase + (uint32_t)(cc * COLS));
+              multi_half(hmb, item0 + 32, tbase + (uint32_t)(cc * COLS + 32));
 #ifdef LGCN_TC_PROF
               ps[4] += 1;
 #endif
@@ -848,6 +964,7 @@ score_topk_tc_kernel(const Params p) {
 #else
             if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
 #endif
+            }
             LGCN_PROF_T(c3t);
             LGCN_PROF_ADD(3, c2t, c3t);
 #ifdef LGCN_TC_PROF
@@ -871,6 +988,7 @@ score_topk_tc_kernel(const Params p) {
                       sel = w.s;
                       pp = w.pp;
                       next_pos = w.next;
+                      ahead_pos = pp + 1 < my_npos ? __ldg(my_pos + pp + 1) : 0x7fffffff;
                     }
                   }
                 }
@@ -898,7 +1016,7 @@ score_topk_tc_kernel(const Params p) {
 #endif
     }
 
-    sel = sel_compact(sel, mv, mi, NT, p.k);
+    sel = sel_finalize(sel, mv, mi, NT, p.k);
     ccnt[t] = sel.cnt;
     if (GROUPS > 1) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
     if (cg == 0 && live) {
