@@ -256,48 +256,46 @@ pack_bf16_kernel(const float* __restrict__ src, const int64_t* __restrict__ ids,
 struct Sel {
   float thr;   // admission threshold: the smallest value of the held top-k set (-inf until k entries exist)
   int cnt;     // entries in the buffer: [0, have) is the set, [have, cnt) were appended since the last fold
-  int have;    // size of the set (<= k); the set is NOT kept sorted (sel_finalize orders it once, at the end)
-  int mp;      // slot of the set's worst entry when have == k
+  int have;    // size of the set (<= k).  Once have == k the set is a binary heap with its WORST entry in slot 0
+               // (smallest value; among equal values the largest id — it arrived last and the final order is
+               // (value desc, id asc)); sel_finalize orders it once, at the end of the sweep.
 };
 
-// Worst entry of the set [0, k): the smallest value; among equal values the largest id (it arrived last, and
-// the final order is (value desc, id asc)).
-__device__ __forceinline__ void sel_scan_min(const float* cval, const int* cidx, int NT, int k, float& minv,
-                                             int& minpos) {
-  // two passes over the values, 8 independent shared-memory loads at a time (a one-entry-at-a-time scan is a
-  // chain of k load latencies: 1200 clocks at k = 20); ids are only read for the entries that tie the minimum
-  float mv = INFINITY;
-  for (int q0 = 0; q0 < k; q0 += 8) {
-    float x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = q0 + i < k ? cval[(q0 + i) * NT] : INFINITY;
-    mv = fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(fminf(x[4], x[5]), fminf(fminf(x[6], x[7]), mv)));
-  }
-  int mid = -1, mpos = 0;
-  for (int q0 = 0; q0 < k; q0 += 8) {
-    float x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = q0 + i < k ? cval[(q0 + i) * NT] : INFINITY;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (x[i] == mv) {
-        const int xi = cidx[(q0 + i) * NT];
-        if (xi > mid) {
-          mid = xi;
-          mpos = q0 + i;
-        }
-      }
-    }
-  }
-  minv = mv;
-  minpos = mpos;
+// true when (av, ai) ranks below (bv, bi) in the final order
+__device__ __forceinline__ bool sel_worse(float av, int ai, float bv, int bi) {
+  return av < bv || (av == bv && ai > bi);
 }
 
-// Fold the appended entries [have, cnt) into the top-k set.  The set is unordered: an admitted entry replaces
-// the worst one and the worst is found again by one scan of k independent loads — the sorted insertion this
-// replaces cost ~14 000 clocks per call (k dependent shared-memory round trips per inserted entry, measured
-// with the LGCN_TC_PROF build).  Appended entries carry larger ids than everything already held, so on an
-// equal value the newcomer loses (strict >).
+// Slot i of the heap [0, k) is vacant: sink (v, id) from there to its place.
+__device__ __forceinline__ void sel_sift_down(float* cval, int* cidx, int NT, int k, int i, float v, int id) {
+  for (;;) {
+    int c = 2 * i + 1;
+    if (c >= k) break;
+    float cv = cval[c * NT];
+    int ci = cidx[c * NT];
+    if (c + 1 < k) {
+      const float dv = cval[(c + 1) * NT];
+      const int di = cidx[(c + 1) * NT];
+      if (sel_worse(dv, di, cv, ci)) {
+        ++c;
+        cv = dv;
+        ci = di;
+      }
+    }
+    if (!sel_worse(cv, ci, v, id)) break;
+    cval[i * NT] = cv;
+    cidx[i * NT] = ci;
+    i = c;
+  }
+  cval[i * NT] = v;
+  cidx[i * NT] = id;
+}
+
+// Fold the appended entries [have, cnt) into the top-k set.  An admitted entry replaces the heap's root (the
+// worst entry held) and sinks: ~log2(k) levels of four independent shared-memory loads.  The sorted insertion
+// this replaces cost ~14 000 clocks per warp-synchronous call (k dependent shared-memory round trips per
+// inserted entry; LGCN_TC_PROF build), a linear scan for the minimum ~10 000.  Appended entries carry larger
+// ids than everything already held, so on an equal value the newcomer loses (strict >).
 __device__ __noinline__ Sel sel_compact(Sel s, float* cval, int* cidx, int NT, int k) {
   int e = s.have;
   if (s.have < k) {   // fill phase: the appended entries sit right behind the set
@@ -308,14 +306,14 @@ __device__ __noinline__ Sel sel_compact(Sel s, float* cval, int* cidx, int NT, i
       s.thr = -INFINITY;
       return s;
     }
-    sel_scan_min(cval, cidx, NT, k, s.thr, s.mp);
+    for (int i = k / 2 - 1; i >= 0; --i) sel_sift_down(cval, cidx, NT, k, i, cval[i * NT], cidx[i * NT]);   // heapify
+    s.thr = cval[0];
   }
   for (; e < s.cnt; ++e) {
     const float v = cval[e * NT];
     if (v > s.thr) {
-      cval[s.mp * NT] = v;
-      cidx[s.mp * NT] = cidx[e * NT];
-      sel_scan_min(cval, cidx, NT, k, s.thr, s.mp);
+      sel_sift_down(cval, cidx, NT, k, 0, v, cidx[e * NT]);
+      s.thr = cval[0];
     }
   }
   s.cnt = k;
@@ -332,7 +330,7 @@ __device__ __noinline__ Sel sel_finalize(Sel s, float* cval, int* cidx, int NT, 
     while (p > 0) {
       const float u = cval[(p - 1) * NT];
       const int ui = cidx[(p - 1) * NT];
-      if (u > v || (u == v && ui < id)) break;
+      if (!sel_worse(u, ui, v, id)) break;
       cval[p * NT] = u;
       cidx[p * NT] = ui;
       --p;
@@ -669,11 +667,10 @@ score_topk_tc_kernel(const Params p) {
     sel.thr = (live && dbg < 3) ? -INFINITY : INFINITY;   // debug 3: max tree only, no candidate ever passes
     sel.cnt = 0;
     sel.have = 0;
-    sel.mp = 0;
     // warp-synchronous compaction once any lane holds k + 6 entries (at most cap - 4): folding early
     // keeps the thresholds tight, and every candidate that is not admitted saves a slow-path trip
     // for the whole warp (trigger 22 / 26 / 30 / 36 / 44 at k = 20: 626 / 663 / 657 / 645 / 632 TFLOP/s)
-    const int trig = p.trig > 0 ? p.trig : min(p.cap - 4, p.k + 6);
+    const int trig = min(p.cap - 4, p.trig > 0 ? p.trig : p.k + 6);
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     // walk of the user's sorted train positives, in step with the item sweep
     int pp = 0;
@@ -906,7 +903,22 @@ score_topk_tc_kernel(const Params p) {
             float second = -INFINITY;
             if (mine) descend<0, 64>(r, r2, m4a, m4b, cma, cmb, cm, second, col);
             const bool multi = mine && second > sel.thr;
-            if (mine && !multi) take(item0 + col, __float_as_uint(cm));
+            if (mine && !multi) {
+              // the lane's only candidate.  No capacity check: entries end with a fold as soon as any lane holds
+              // `trig` (<= cap - 4) entries and this path appends one, so the buffer cannot be full here.
+              const int item = item0 + col;
+              while (next_pos < item) {   // walk of the sorted train positives (ascending sweep)
+                ++pp;
+                next_pos = ahead_pos;
+                ahead_pos = pp + 1 < my_npos ? __ldg(my_pos + pp + 1) : 0x7fffffff;
+              }
+              const float v = next_pos == item ? p.mask_value : cm;  // trainer.py:137
+              if (item < p.m_items && v > sel.thr) {   // item >= m_items: zero padding of the last tile
+                mv[sel.cnt * NT] = v;
+                mi[sel.cnt * NT] = item;
+                ++sel.cnt;
+              }
+            }
 #ifdef LGCN_TC_PROF
             __syncwarp();
             const long long s1 = clock64();

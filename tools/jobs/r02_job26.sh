@@ -1,0 +1,14 @@
+#!/bin/bash
+# round-2 job 26 (1 GPU): heap-ordered top-k set — parity, A-B, compaction trigger sweep, phase profile
+O=gpurun_out/r02z; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_tc.py tests/test_gpu_cfg2.py tests/test_gpu_parity.py -q -x > $O/test_tc.log 2>&1; echo "rc=$?" >> $O/test_tc.log
+SW="timeout 120 python tools/topk_sweep.py --users 75776 --items 2000000"
+P=$PWD/furusato_recommend_b200/liblgcn_b200_tcprof.so
+$SW > $O/sweep_default.log 2>&1
+$SW --k 1 > $O/sweep_k1.log 2>&1
+$SW --k 10 > $O/sweep_k10.log 2>&1
+$SW --d 128 > $O/sweep_d128.log 2>&1
+$SW --d 128 --k 50 > $O/sweep_d128_k50.log 2>&1
+for t in 22 24 28 32; do LGCN_TC_TRIG=$t $SW > $O/sweep_trig$t.log 2>&1; done
+LGCN_B200_LIB=$P $SW > $O/prof_default.log 2>&1
+tail -n 3 $O/test_tc.log; for f in $O/sweep_*.log; do echo "$(basename $f .log): $(tail -n 1 $f)"; done; head -n 5 $O/prof_default.log | cut -c1-300
