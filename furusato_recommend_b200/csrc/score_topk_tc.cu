@@ -814,8 +814,22 @@ score_topk_tc_kernel(const Params p) {
     long long ps[6] = {0, 0, 0, 0, 0, 0};
     const long long pf_begin = clock64();
 #endif
+    // Early hand-back.  With two TMEM stages per user tile the time a stage is HELD (accumulator full -> all four
+    // warps done) bounds the whole pipeline (clock64 timeline, profiles/r02_tc_prof_timeline.log: issue 300-540,
+    // commit -> epilogue 230-500, hold ~800, hand-back -> issuer 140 clocks per stage cycle).  Once every row of
+    // the warp holds k entries (`warm`, warp-uniform) the stage goes back right after the LAST chunk's
+    // tcgen05.ld completed: that chunk's max tree, vote and candidate handling work on registers only (the
+    // rare several-candidates-in-one-lane case then picks its values with a per-lane switch instead of the
+    // TMEM re-read), so half of all candidate entries leave the critical path.
+    // Measured (profiles/r02_tc_experiments.log, job r02ac): +5 % at d = 128 (965 -> 1011 TFLOP/s), but -4 % at
+    // d = 64 — there the next MMA then overlaps the other stage's read-out and the tcgen05.ld wait grows from
+    // 78 to 189 clocks per tile (TMEM port contention between the accumulating MMA and the loads) — so it is
+    // compiled in for d >= 128 only.
+    constexpr bool kEarlyHandBack = !ACC16 && D >= 128;
+    bool warm = dbg == 3;
     for (int j = 0; j < n_tiles; ++j) {
       const int a = j % NST;
+      bool released = false;
       LGCN_PROF_T(q0);
       mbar_wait_hint(bar_tfull + 8 * (a * MT + mt), (j / NST) & 1, p.wait_hint);
       LGCN_PROF_T(q1);
@@ -836,6 +850,12 @@ score_topk_tc_kernel(const Params p) {
           tc_ld32(tbase + (uint32_t)(cc * COLS + 32), r2);
         }
         tc_wait_ld();
+        if (kEarlyHandBack && warm && cc == CPG - 1) {   // warp-uniform
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * (a * MT + mt));
+          released = true;
+        }
         LGCN_PROF_T(c1t);
         LGCN_PROF_ADD(1, c0t, c1t);
         LGCN_STAMP(j, 3, blockIdx.x == 0 && ew == 0 && lane == 0);
@@ -961,8 +981,30 @@ score_topk_tc_kernel(const Params p) {
                   if (two && ((hm >> cb) & 1u)) take(item_base + cb, rb);
                 }
               };
-              multi_half(hma, item0, tbase + (uint32_t)(cc * COLS));
-              multi_half(hmb, item0 + 32, tbase + (uint32_t)(cc * COLS + 32));
+              if (!released) {
+                multi_half(hma, item0, tbase + (uint32_t)(cc * COLS));
+                multi_half(hmb, item0 + 32, tbase + (uint32_t)(cc * COLS + 32));
+              } else if (multi) {
+                // the stage is gone: per-lane walk of the hit columns, values picked from the registers by a dense switch
+                auto multi_regs = [&](uint32_t hm, const uint32_t(&x)[32], int item_base) {
+                  while (hm) {
+                    const int c = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    uint32_t raw = 0;
+                    switch (c) {
+#define LGCN_PICK(i) case i: raw = x[i]; break;
+                      LGCN_PICK(0) LGCN_PICK(1) LGCN_PICK(2) LGCN_PICK(3) LGCN_PICK(4) LGCN_PICK(5) LGCN_PICK(6) LGCN_PICK(7)
+                      LGCN_PICK(8) LGCN_PICK(9) LGCN_PICK(10) LGCN_PICK(11) LGCN_PICK(12) LGCN_PICK(13) LGCN_PICK(14) LGCN_PICK(15)
+                      LGCN_PICK(16) LGCN_PICK(17) LGCN_PICK(18) LGCN_PICK(19) LGCN_PICK(20) LGCN_PICK(21) LGCN_PICK(22) LGCN_PICK(23)
+                      LGCN_PICK(24) LGCN_PICK(25) LGCN_PICK(26) LGCN_PICK(27) LGCN_PICK(28) LGCN_PICK(29) LGCN_PICK(30) LGCN_PICK(31)
+#undef LGCN_PICK
+                    }
+                    take(item_base + c, raw);
+                  }
+                };
+                multi_regs(hma, r, item0);
+                multi_regs(hmb, r2, item0 + 32);
+              }
 #ifdef LGCN_TC_PROF
               ps[4] += 1;
 #endif
@@ -971,10 +1013,17 @@ score_topk_tc_kernel(const Params p) {
             const long long s3 = clock64();
             ps[2] += s3 - s2;
             const bool do_compact = __any_sync(0xffffffffu, sel.cnt >= trig);
-            if (do_compact) { sel = sel_compact(sel, mv, mi, NT, p.k); ps[5] += 1; }
+            if (do_compact) {
+              sel = sel_compact(sel, mv, mi, NT, p.k);
+              ps[5] += 1;
+              if (!warm) warm = __all_sync(0xffffffffu, sel.have == p.k || !live);
+            }
             ps[3] += clock64() - s3;
 #else
-            if (__any_sync(0xffffffffu, sel.cnt >= trig)) sel = sel_compact(sel, mv, mi, NT, p.k);
+            if (__any_sync(0xffffffffu, sel.cnt >= trig)) {
+              sel = sel_compact(sel, mv, mi, NT, p.k);
+              if (!warm) warm = __all_sync(0xffffffffu, sel.have == p.k || !live);
+            }
 #endif
             }
             LGCN_PROF_T(c3t);
@@ -1012,9 +1061,11 @@ score_topk_tc_kernel(const Params p) {
       }
       // one arrival per warp (128 same-address mbarrier arrives per hand-off serialise in shared memory)
       LGCN_PROF_T(q4);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * (a * MT + mt));
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * (a * MT + mt));
+      }
       LGCN_PROF_T(q5);
       LGCN_PROF_ADD(4, q4, q5);
       LGCN_STAMP(j, 4, blockIdx.x == 0 && ew == 0 && lane == 0);
