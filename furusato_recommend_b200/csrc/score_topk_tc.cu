@@ -11,21 +11,26 @@
 //                  i.e. 8x16 B core matrices, SBO = 128 B, LBO = rows*16 B.
 //   warp 0         producer: one cp.async.bulk per tile (16/32 KB) -> smem ring,
 //                  completion on an mbarrier (expect_tx).
-//   warp 1         one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//                  (M=128, N=TN, K=16) d/16 times per tile into one of two TMEM
-//                  accumulator stages; tcgen05.commit frees the smem stage and
-//                  publishes the accumulator.
+//   warps 1 (, 3)  MMA issuers, one warp per user tile: the whole warp runs the loop and an
+//                  elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=TN, K=16)
+//                  d/16 times per tile into one of two TMEM accumulator stages; tcgen05.commit
+//                  frees the smem stage and publishes the accumulator.
 //   warp 2         allocates / frees the 2*TN TMEM columns.
-//   warps 4..      epilogue: thread == TMEM lane == user row.  tcgen05.ld 32
-//                  columns at a time; a max-tree against the row's running
-//                  threshold rejects almost every chunk in ~1 op per score;
-//                  survivors are checked against the user's train positives
-//                  (binary search) and appended to a per-row shared-memory
-//                  buffer that is compacted warp-synchronously to the sorted
-//                  top-k.  Train positives are masked by walking the user's sorted
-//                  list in step with the sweep.  Two epilogue groups split the columns
-//                  of every tile and are merged at the end (k <= 24); one group for
-//                  larger k.  The other accumulator stage is being filled meanwhile.
+//   warps 4..      epilogue: thread == TMEM lane == user row.  tcgen05.ld 64 columns at a
+//                  time; two trees of 3-input maxima against the row's running threshold and
+//                  one warp vote reject almost every chunk in ~0.6 instructions per score.
+//                  Candidate path (some lane has a score above its threshold): the lane finds
+//                  the column of its chunk maximum by descent through the maxima the fast path
+//                  already holds and appends it; the chunk's second largest value tells whether
+//                  the lane has more candidates (rare: those columns are re-read from TMEM).
+//                  The per-row shared-memory buffer keeps the top-k set as a binary heap with the
+//                  worst entry at the root (fold = replace-root + sift-down, warp-synchronous);
+//                  the set is ordered once, at the end of the sweep.  Train positives are masked
+//                  by walking the user's sorted list in step with the sweep, one load ahead.
+//                  Layout m2g2 (default, k <= 24, d <= 64): two user tiles per CTA, one epilogue
+//                  group of 4 warps per user tile; other layouts split the columns of a tile
+//                  over two groups and merge at the end.  The other accumulator stage is being
+//                  filled meanwhile.  DESIGN.md 4.4 has the measurements behind each choice.
 // Ties: items arrive in ascending id inside a thread, filters are strict, the
 // final merge orders by (score desc, id asc) => lowest id wins, as in the fp32 path.
 #include <cuda_fp16.h>
@@ -490,10 +495,10 @@ struct Params {
 // NST accumulator stages in TMEM: an epilogue warp that runs into candidates (the rare slow path)
 // only holds back ITS stage; with 4 stages the other warps and the MMA issuer run ahead and the
 // variance averages out instead of costing every tile the slowest warp's time.
-// RS ("register-staged", EXPERIMENTAL, not the default — untested on hardware at the end of round 1):
-// the epilogue copies the whole 128-column accumulator of its user tile into registers and hands the
-// TMEM stage back BEFORE any selection work, so the MMA never waits for a warp that ran into
-// candidates; candidate values are then picked from registers with a warp-uniform switch.
+// RS ("register-staged", layout "m2rl", opt-in): the epilogue copies the whole 128-column accumulator of its
+// user tile into registers and hands the TMEM stage back BEFORE any selection work; candidates are handled
+// lane-locally from the registers.  Parity-tested; slower than m2g2 at d = 64 (the next MMA then overlaps the
+// other stage's read-out: TMEM port contention).
 // CL > 1 ("m2c2" / "m2c4"): CL CTAs form a thread-block cluster that SHARES the item-tile stream — every
 // CTA keeps its own users, accumulators and epilogue, but each item tile is fetched from L2 once per
 // cluster (CTA r loads slice r and multicasts it), and a ring stage is recycled when the MMAs of all CL
@@ -1264,14 +1269,15 @@ static int run_cfg(const float* user_emb, const float* item_emb, const int64_t* 
 
 // Configuration choice.  TN1 = item-tile width of the one-user-tile layouts (256; 128 at d = 128).
 // Layout names (LGCN_TC_LAYOUT overrides the automatic choice for A-B runs); measured at
-// 75 776 users x 2 M items, d = 64, k = 20 (gpurun_out/tc*_sweep.log):
+// 75 776 users x 2 M items, d = 64, k = 20 with the final candidate path (profiles/r02_tc_experiments.log):
 //   m2g2  MT = 2 user tiles x TN = 128, one epilogue group per user tile, 6-deep operand ring
-//         (default for k <= 24, d <= 64, fp32 accumulators)                       605-610 TFLOP/s
-//   m2g4  the same with two column groups per user tile (16 epilogue warps, k <= 20)   545
-//   g2    one user tile x TN1, two column groups (the round-1 layout)                   494-505
-//   g4    one user tile x TN1, four column groups                                       443
-// Four TMEM accumulator stages (NST = 4: one user tile x TN 128, or two x TN 64) were slower
-// (433-444): the smaller tiles pay the per-tile hand-off more often.  24 < k <= 112: one group.
+//         (default for k <= 24, d <= 64, fp32 accumulators)                           1054-1061 TFLOP/s
+//   m2g4  the same with two column groups per user tile (16 epilogue warps, k <= 20)       865
+//   m2rl  m2g2 with the register-staged epilogue                                           740-786
+//   m2s4  four TMEM stages x 64-column tiles (N = 64 MMAs are issue bound)                 698 (mid-round)
+//   m2c2 / m2c4  m2g2 in clusters of 2 / 4 CTAs sharing the item-tile stream (multicast)   770 / 415 (mid-round)
+//   g2    one user tile x TN1, two column groups (the round-1 layout; d = 128 uses it)     560 (mid-round)
+// 24 < k <= 112: one group.
 template <int D, int TN1>
 static int run(const float* user_emb, const float* item_emb, const int64_t* user_ids, int n_eval,
                int m_items, const int64_t* pos_rowptr, const int32_t* pos_sorted, int k,
