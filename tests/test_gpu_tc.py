@@ -41,6 +41,9 @@ def _case(U, m, d, seed, quantise=False, dense_pos=False):
 @pytest.mark.parametrize("shape", [
     (300, 400, 32, 20, False), (1000, 5000, 64, 20, True), (257, 1111, 128, 20, False),
     (130, 700, 64, 50, False), (64, 40, 64, 20, False), (128, 256, 64, 1, False), (129, 513, 64, 24, True),
+    # long sweeps: the candidate path after warm-up (argmax descent, several equal maxima in one chunk, heap
+    # folds) and, at d = 128, the early hand-back of the TMEM stage with values picked from registers
+    (300, 50000, 64, 20, True), (200, 30000, 128, 20, True), (260, 40000, 128, 5, False),
 ])
 @pytest.mark.parametrize("prec", ["bf16", "f16"])
 def test_tensor_core_topk(shape, prec):
