@@ -659,6 +659,31 @@ def eigen_parity(model, ds, world: int, rank: int, dev: str) -> dict:
             "max_rel_err": err, "tolerance": tol, "ok": bool(err < tol)}
 
 
+def shared_device_graph(W: dict, dev: str, rank: int, world: int):
+    """The synthetic graph of a big workload, generated ON THE DEVICE by rank 0 and broadcast.  Every rank used to
+    generate its own copy; at cfg-3 size the torch device ops of the recipe are not bit-reproducible (same n, m and
+    edge count, a handful of different edges per call — tools/debug_graph_determinism.py), so the ranks of a
+    row-partitioned model would each cut their rows out of a slightly different graph."""
+    import torch
+    import torch.distributed as dist
+    from furusato_recommend_b200.synthetic import bipartite
+    if world == 1:
+        return bipartite(W["n_users"], W["m_items"], W["n_interactions"], seed=W["seed"], device=dev)
+    meta = torch.zeros(4, dtype=torch.int64, device=dev)
+    parts = None
+    if rank == 0:
+        n, m, tu, ti, su, si = bipartite(W["n_users"], W["m_items"], W["n_interactions"], seed=W["seed"], device=dev)
+        meta = torch.tensor([n, m, tu.numel(), su.numel()], dtype=torch.int64, device=dev)
+        parts = [tu, ti, su, si]
+    dist.broadcast(meta, 0)
+    n, m, n_tr, n_te = (int(x) for x in meta.tolist())
+    if rank != 0:
+        parts = [torch.empty(k, dtype=torch.int64, device=dev) for k in (n_tr, n_tr, n_te, n_te)]
+    for t in parts:
+        dist.broadcast(t, 0)
+    return (n, m, *parts)
+
+
 def run_cfg3_block(args, rank: int, world: int, local_rank: int) -> dict:
     """BASELINE configs[2]: 10 M users x 2 M items x 500 M train edges, d = 128, K = 3 — ONE graph, rows
     partitioned over the ranks (strong scaling).  Its embedding table is 6.1 GB, so the SpMM is HBM-bound:
@@ -670,7 +695,7 @@ def run_cfg3_block(args, rank: int, world: int, local_rank: int) -> dict:
     dev = f"cuda:{local_rank}"
     W = dict(CFG3 if args.cfg3_shape == "cfg3" else HBM)
     t_build = time.perf_counter()
-    n, m, tu, ti, su, si = bipartite(W["n_users"], W["m_items"], W["n_interactions"], seed=W["seed"], device=dev)
+    n, m, tu, ti, su, si = shared_device_graph(W, dev, rank, world)
     cfg = dict(recdim=W["d"], layer=W["layers"], lr=W["lr"], decay=W["decay"], bpr_batch_size=W["batch"], device=dev,
                test_u_batch_size=10000, storage_dtype=args.storage, dist_exchange=args.exchange,
                dist_partition=args.partition)
@@ -751,7 +776,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     big = args.workload in ("hbm", "cfg3", "cfg4")
     if big:
         from furusato_recommend_b200.dataloader import DeviceDataset
-        n, m, tu, ti, su, si = bipartite(W["n_users"], W["m_items"], W["n_interactions"], seed=W["seed"], device=dev)
+        n, m, tu, ti, su, si = shared_device_graph(W, dev, rank, world)
         ds = DeviceDataset(n, m, tu, ti, su, si, config=cfg)
         args.no_eval = args.no_cpu_baseline = args.no_cfg3 = args.no_library_bar = args.no_bf16_block = True
         args.no_parity = True

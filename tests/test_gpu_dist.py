@@ -147,3 +147,59 @@ def test_partial_batch_between_graph_replays_2gpu(exchange):
             for a, b in zip(losses, ref):
                 assert abs(a - b) < 1e-5 * abs(b), (losses, ref)
             assert e_emb < 1e-6, e_emb
+
+
+def _worker_user_heavy(rank, world, port, ret):
+    """dist_partition='auto' on a user-heavy graph (6000 users x 500 items): the reduce partition is picked
+    (parallel.DistLightGCN, measured on cfg-3) and two steps agree with the single-GPU model."""
+    import torch.distributed as dist
+    from furusato_recommend_b200 import LightGCN
+    from furusato_recommend_b200.dataloader import BasicDataset
+    from furusato_recommend_b200.parallel import DistLightGCN
+    from furusato_recommend_b200.synthetic import bipartite
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        n, m, tu, ti, su, si = bipartite(6000, 500, 120_000, seed=5)
+        B = 512
+        cfg = dict(recdim=64, layer=3, lr=1e-3, decay=1e-4, bpr_batch_size=B, device=dev, test_u_batch_size=128)
+        ds = BasicDataset(n, m, tu.numpy(), ti.numpy(), su.numpy(), si.numpy(), config=cfg, device=dev)
+        gen = torch.Generator().manual_seed(3)
+        E0 = (torch.randn(n + m, 64, generator=gen) * 0.1).to(dev)
+        u = torch.randint(0, n, (B,), generator=gen).to(dev)
+        p = torch.randint(0, m, (B,), generator=gen).to(dev)
+        q = torch.randint(0, m, (B,), generator=gen).to(dev)
+        sm = LightGCN(cfg, ds)
+        with torch.no_grad():
+            sm.all_embedding.weight.copy_(E0)
+        sm.train()
+        dm = DistLightGCN(cfg, ds, rank, world)
+        dm.load_global_embedding(E0)
+        light = dm.part.unshard(_gather(dm, dm.computer_local()))
+        with torch.no_grad():
+            ref = torch.cat(sm.computer())
+        e_prop = float((light - ref).abs().max() / ref.abs().max())
+        losses = [float(dm.fused_step(u, p, q)) for _ in range(2)]
+        refl = [float(sm.stageOne(u, p, q)) for _ in range(2)]
+        e_emb = float((dm.gather_embedding() - sm.all_embedding.weight.detach()).abs().max())
+        ret[rank] = (bool(dm.reduce_mode), e_prop, losses, refl, e_emb)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.timeout(120)
+def test_auto_partition_keeps_user_rows_home_on_a_user_heavy_graph_2gpu():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_user_heavy, args=(world, port, ret), nprocs=world, join=True)
+        for rank in range(world):
+            reduce_mode, e_prop, losses, refl, e_emb = ret[rank]
+            assert reduce_mode
+            assert e_prop < 1e-5, e_prop
+            for a, b in zip(losses, refl):
+                assert abs(a - b) < 1e-5 * abs(b), (losses, refl)
+            assert e_emb < 1e-6, e_emb
