@@ -41,9 +41,12 @@ def bipartite(n_users: int, m_items: int, n_interactions: int, seed: int = 2020,
     deg = (deg * (n_interactions / float(deg.sum()))).clamp_(min=core + 1, max=min(2000, m_items // 2))
     deg = deg.round().long()
     # item popularity CDF under a random permutation
-    rank = torch.arange(1, m_items + 1, device=dev, dtype=torch.float64)
+    # built on the HOST: a device cumsum (decoupled look-back scan) associates floating-point sums differently from
+    # call to call, and a CDF that differs in its last bits flips a handful of the ~10^9 searchsorted draws below —
+    # two ranks generating "the same" cfg-3 graph then disagree about a few edges
+    rank = torch.arange(1, m_items + 1, dtype=torch.float64)
     p = rank.pow(-0.8)
-    cdf = torch.cumsum(p / p.sum(), 0)
+    cdf = torch.cumsum(p / p.sum(), 0).to(dev)
     perm = torch.randperm(m_items, generator=g, device=dev)
     # oversampled candidate draws, then de-duplicate (user,item) pairs
     over = (deg.double() * 1.6).ceil().long() + 8
