@@ -347,13 +347,8 @@ __device__ __noinline__ Sel sel_finalize(Sel s, float* cval, int* cidx, int NT, 
   return s;
 }
 
-// Per-thread walk of the user's sorted train positives.  Candidates reach sel_append in
-// ascending item id, so membership is a pointer advance, not a search.
-struct PosWalk {
-  const int32_t* pos;
-  int n, pp, next;
-};
-
+// State handed back by sel_append (f16-accumulator path): the candidate buffer and the walk of the user's sorted
+// train positives.  Candidates arrive in ascending item id, so membership is a pointer advance, not a search.
 struct SelWalk {
   Sel s;
   int pp, next;
