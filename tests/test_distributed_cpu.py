@@ -204,3 +204,33 @@ def test_reduce_partition_graphs_reproduce_the_propagation(world):
         got[lo:hi] = csr.dinv.double()[lo:hi, None] * partial_sum[b * R_i:b * R_i + (hi - lo)]
         assert float(partial_sum[b * R_i + (hi - lo):(b + 1) * R_i].abs().sum()) == 0.0   # padding rows stay empty
     assert float((got - want).abs().max()) < 1e-6 * float(want.abs().max())
+
+
+def _worker_shared_graph(rank, world, port, ret):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    import bench
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        W = dict(n_users=1500, m_items=400, n_interactions=40_000, seed=9)
+        n, m, tu, ti, su, si = bench.shared_device_graph(W, "cpu", rank, world)
+        ret[rank] = (n, m, tu.clone(), ti.clone(), su.clone(), si.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_big_graphs_are_generated_once_and_broadcast():
+    """bench.shared_device_graph: rank 0 generates, every rank receives the same tensors (gloo, world 2) — the
+    ranks of a row-partitioned model must cut their rows out of ONE graph."""
+    from furusato_recommend_b200.synthetic import bipartite
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_shared_graph, args=(world, port, ret), nprocs=world, join=True)
+        ref = bipartite(1500, 400, 40_000, seed=9)
+        for rank in range(world):
+            got = ret[rank]
+            assert got[0] == ref[0] and got[1] == ref[1]
+            for a, b in zip(got[2:], ref[2:]):
+                assert torch.equal(a, b)
